@@ -1,0 +1,1 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): empty stand-in
