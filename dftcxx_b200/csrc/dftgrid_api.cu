@@ -1,0 +1,731 @@
+// C ABI (include/dftgrid.h) and host orchestration of the B200 grid engine.
+// All compute runs in the hand-written sm_100a kernels of kernels_*.cuh; there is no CPU path.
+#include "../../include/dftgrid.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "host_tables.h"
+#include "kernels_dense.cuh"
+#include "kernels_grid.cuh"
+#include "kernels_hartree.cuh"
+#include "nccl_dyn.h"
+
+using namespace dfg;
+
+namespace {
+
+thread_local std::string g_error;
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess)                                                                                     \
+            throw CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +   \
+                            std::to_string(__LINE__) + ")");                                                      \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T>& v, cudaStream_t s) {
+        alloc(v.size());
+        if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void zero(cudaStream_t s) {
+        if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct dftgrid {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    bool built = false, have_density = false, have_potential = false, contract_valid = false, timed_iter = false;
+    long launches = 0;
+
+    // host description
+    int natoms = 0, nbf = 0, nbp = 0, nprim = 0;
+    std::vector<int> Z;
+    std::vector<double> atom_xyz;
+    double zsum = 0.0;
+    dftgrid_params prm{};
+    GridShape g{};
+    int leb_off = 0;
+
+    // basis (host, column order)
+    std::vector<double> center_xyz, exp_alpha, prim_coeff, prim_norm;
+    std::vector<int> bf_center, bf_prim_off, center_exp_off, prim_exp, prim_lmn;
+
+    // device: static tables
+    DevBuf<double> d_atom_xyz, d_Rdist, d_rtab, d_wrad, d_leb, d_Y, d_Yt, d_pre, d_lu, d_xs;
+    DevBuf<int> d_perm, d_lo, d_hi;
+    DevBuf<double> d_spA, d_spCp, d_spDen, d_spH, d_spRh;
+    SplineDev spline{};
+    LdaConstants lda{};
+    DevBuf<double> d_center_xyz, d_exp_alpha, d_prim_coeff, d_prim_norm;
+    DevBuf<int> d_bf_center, d_bf_prim_off, d_center_exp_off, d_prim_exp, d_prim_lmn;
+
+    // device: per point
+    DevBuf<double> d_x, d_y, d_z, d_w, d_wb, d_rho, d_dxc, d_exw, d_V, d_Vown, d_dJ, d_phi;
+    // device: per iteration
+    DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
+    DevBuf<int> d_pairs;
+    int npairs = 0, nsplit = 1;
+
+    // pinned staging
+    double* h_P = nullptr;
+    double* h_res = nullptr;
+
+    // comm
+    NcclComm comm = nullptr;
+
+    // timing
+    cudaEvent_t ev[16]{};
+    bool ev_build = false, ev_iter = false;
+    double t_ms[DFTGRID_T_COUNT]{};
+
+    ~dftgrid() {
+        if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (h_P) cudaFreeHost(h_P);
+        if (h_res) cudaFreeHost(h_res);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+void allreduce(dftgrid* h, double* buf, size_t count) {
+    if (h->nranks == 1) return;
+    if (!h->comm) throw std::runtime_error("nranks > 1 but dftgrid_comm_init was not called");
+    int rc = nccl_api().AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
+    if (rc != 0) throw std::runtime_error(std::string("ncclAllReduce failed: ") + nccl_api().GetErrorString(rc));
+}
+
+void prepare_basis(dftgrid* h, const dftgrid_system* s) {
+    // unique centres (exact coordinate match) and, per centre, the distinct exponents
+    h->nbf = s->nbf;
+    h->nbp = round_up(std::max(s->nbf, 1), kNbAlign);
+    h->nprim = s->nprim;
+    std::vector<std::vector<double>> cexp;
+    h->bf_center.resize(s->nbf);
+    h->bf_prim_off.assign(s->nbf + 1, 0);
+    std::vector<int> prim_center(s->nprim), prim_local(s->nprim);
+    int k = 0;
+    for (int b = 0; b < s->nbf; b++) {
+        const double* c = s->bf_center + 3 * b;
+        int ci = -1;
+        // consecutive CGFs normally share a centre: test the most recent ones first
+        for (int t = (int)h->center_xyz.size() / 3 - 1; t >= 0; t--)
+            if (h->center_xyz[3 * t] == c[0] && h->center_xyz[3 * t + 1] == c[1] && h->center_xyz[3 * t + 2] == c[2]) {
+                ci = t;
+                break;
+            }
+        if (ci < 0) {
+            ci = (int)h->center_xyz.size() / 3;
+            h->center_xyz.insert(h->center_xyz.end(), c, c + 3);
+            cexp.emplace_back();
+        }
+        h->bf_center[b] = ci;
+        if (s->bf_nprim[b] < 0) throw std::runtime_error("negative primitive count");
+        for (int j = 0; j < s->bf_nprim[b]; j++, k++) {
+            if (k >= s->nprim) throw std::runtime_error("sum(bf_nprim) exceeds nprim");
+            const int l = s->lmn[3 * k], m = s->lmn[3 * k + 1], n = s->lmn[3 * k + 2];
+            if (l < 0 || m < 0 || n < 0 || l + m + n > 2) throw std::runtime_error("Undefined orbital type (l+m+n > 2)");
+            auto& ev = cexp[ci];
+            int u = -1;
+            for (size_t t = 0; t < ev.size(); t++)
+                if (ev[t] == s->alpha[k]) u = (int)t;
+            if (u < 0) {
+                u = (int)ev.size();
+                ev.push_back(s->alpha[k]);
+            }
+            prim_center[k] = ci;
+            prim_local[k] = u;
+            h->prim_coeff.push_back(s->coeff[k]);
+            h->prim_norm.push_back(s->norm[k]);
+            h->prim_lmn.push_back(l | (m << 4) | (n << 8));
+        }
+        h->bf_prim_off[b + 1] = k;
+    }
+    if (k != s->nprim) throw std::runtime_error("sum(bf_nprim) != nprim");
+    h->center_exp_off.assign(cexp.size() + 1, 0);
+    for (size_t c = 0; c < cexp.size(); c++) {
+        if ((int)cexp[c].size() > kPhiMaxExp) throw std::runtime_error("too many distinct exponents on one centre");
+        h->center_exp_off[c + 1] = h->center_exp_off[c] + (int)cexp[c].size();
+        h->exp_alpha.insert(h->exp_alpha.end(), cexp[c].begin(), cexp[c].end());
+    }
+    h->prim_exp.resize(s->nprim);
+    for (int t = 0; t < s->nprim; t++) h->prim_exp[t] = h->center_exp_off[prim_center[t]] + prim_local[t];
+}
+
+void record(dftgrid* h, int i) { CK(cudaEventRecord(h->ev[i], h->stream)); }
+
+float elapsed(dftgrid* h, int a, int b) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]));
+    return ms;
+}
+
+void do_build(dftgrid* h) {
+    const dftgrid_params& prm = h->prm;
+    if (prm.lebedev_order < 0 || prm.lebedev_order > 10) throw std::runtime_error("lebedev_order must be 0..10");
+    if (prm.lmax < 0 || prm.lmax > kMaxL) throw std::runtime_error("lmax out of range");
+    cudaStream_t st = h->stream;
+    GridShape& g = h->g;
+    g.natoms = h->natoms;
+    g.nrad = prm.radial_points;
+    g.nang = kLebedevCounts[prm.lebedev_order];
+    g.lmax = prm.lmax;
+    g.nlm = (prm.lmax + 1) * (prm.lmax + 1);
+    g.npts = (long)g.natoms * g.nrad * g.nang;
+    const long nshell = (long)g.natoms * g.nrad;
+    g.shell0 = nshell * h->rank / h->nranks;
+    g.nshell_loc = nshell * (h->rank + 1) / h->nranks - g.shell0;
+    g.nloc = g.nshell_loc * g.nang;
+    h->leb_off = lebedev_offset(prm.lebedev_order);
+
+    // ---- host tables
+    std::vector<double> r, wr, Y, pre;
+    make_radial(g.nrad, r, wr);
+    make_ylm_table(h->leb_off, g.nang, g.lmax, Y, pre);
+    std::vector<double> Yt((size_t)g.nang * g.nlm);
+    for (int j = 0; j < g.nang; j++)
+        for (int lm = 0; lm < g.nlm; lm++) Yt[(size_t)lm * g.nang + j] = Y[(size_t)j * g.nlm + lm];
+    PoissonLU lu;
+    make_poisson_lu(g.nrad, g.lmax, r, lu);
+    SplineSystem sp;
+    make_spline_system(g.nrad, r, sp);
+    make_lda_constants(h->lda);
+    std::vector<double> leb((size_t)g.nang * 4);
+    for (int j = 0; j < g.nang; j++)
+        for (int c = 0; c < 4; c++) leb[4 * j + c] = kLebedevTable[h->leb_off + j][c];
+    std::vector<double> Rdist((size_t)g.natoms * g.natoms, 0.0);
+    for (int a = 0; a < g.natoms; a++)
+        for (int b = 0; b < g.natoms; b++) {
+            // (p2 - p1).norm() of src/moleculargrid.cpp:291-293; symmetric in (a,b) bit for bit
+            const double dx = h->atom_xyz[3 * b] - h->atom_xyz[3 * a], dy = h->atom_xyz[3 * b + 1] - h->atom_xyz[3 * a + 1],
+                         dz = h->atom_xyz[3 * b + 2] - h->atom_xyz[3 * a + 2];
+            Rdist[(size_t)a * g.natoms + b] = std::sqrt(dx * dx + dy * dy + dz * dz);
+        }
+
+    h->d_atom_xyz.upload(h->atom_xyz, st);
+    h->d_Rdist.upload(Rdist, st);
+    h->d_rtab.upload(r, st);
+    h->d_wrad.upload(wr, st);
+    h->d_leb.upload(leb, st);
+    h->d_Y.upload(Y, st);
+    h->d_Yt.upload(Yt, st);
+    h->d_pre.upload(pre, st);
+    h->d_lu.upload(lu.lu, st);
+    h->d_perm.upload(lu.perm, st);
+    h->d_lo.upload(lu.lo, st);
+    h->d_hi.upload(lu.hi, st);
+    h->d_xs.upload(sp.x, st);
+    h->d_spA.upload(sp.A, st);
+    h->d_spCp.upload(sp.Cp, st);
+    h->d_spDen.upload(sp.den, st);
+    h->d_spH.upload(sp.h, st);
+    h->d_spRh.upload(sp.rh, st);
+    h->spline = SplineDev{h->d_xs.p, h->d_spA.p, h->d_spCp.p, h->d_spDen.p, h->d_spH.p, h->d_spRh.p,
+                          sp.first_w[0], sp.first_w[1], sp.last_w[0], sp.last_w[1]};
+    h->d_center_xyz.upload(h->center_xyz, st);
+    h->d_exp_alpha.upload(h->exp_alpha, st);
+    h->d_prim_coeff.upload(h->prim_coeff, st);
+    h->d_prim_norm.upload(h->prim_norm, st);
+    h->d_bf_center.upload(h->bf_center, st);
+    h->d_bf_prim_off.upload(h->bf_prim_off, st);
+    h->d_center_exp_off.upload(h->center_exp_off, st);
+    h->d_prim_exp.upload(h->prim_exp, st);
+    h->d_prim_lmn.upload(h->prim_lmn, st);
+
+    // ---- per-point storage
+    const size_t nl = (size_t)g.nloc, nlp = nl + 64;
+    h->d_x.alloc(nlp);
+    h->d_y.alloc(nlp);
+    h->d_z.alloc(nlp);
+    h->d_w.alloc(nlp);
+    h->d_wb.alloc(nlp);
+    h->d_rho.alloc(nlp);
+    h->d_dxc.alloc(nlp);
+    h->d_exw.alloc(nlp);
+    h->d_V.alloc(nlp);
+    h->d_Vown.alloc(nlp);
+    h->d_dJ.alloc(nlp);
+    h->d_dxc.zero(st);
+    h->d_dJ.zero(st);
+    h->d_phi.alloc(nl * h->nbp + 64);
+    const size_t nsys = (size_t)g.natoms * g.nlm;
+    h->d_P.alloc((size_t)h->nbp * h->nbp);
+    h->d_P.zero(st);
+    h->d_Praw.alloc((size_t)h->nbf * h->nbf);
+    h->d_shell_raw.alloc((size_t)nshell);
+    h->d_shell2.alloc((size_t)nshell * 2 + (size_t)nshell * g.nlm);  // [shell sums (2 per shell) | rho_lm] contiguous: one collective
+    h->d_qatom.alloc(g.natoms);
+    h->d_scalars.alloc(4);
+    h->d_U_lm.alloc((size_t)nshell * g.nlm);
+    h->d_work.alloc(std::max((size_t)(g.nrad + 2) * nsys, (size_t)2 * g.nrad * nsys));
+    h->d_coef.alloc((size_t)g.natoms * g.nrad * g.nlm * 4);
+    h->d_res.alloc((size_t)2 * h->nbf * h->nbf + 2);
+
+    // ---- contraction tiling
+    const int nt = (h->nbp + kTileM - 1) / kTileM;
+    std::vector<int> pairs;
+    for (int i = 0; i < nt; i++)
+        for (int j = i; j < nt; j++) {
+            pairs.push_back(i);
+            pairs.push_back(j);
+        }
+    h->npairs = (int)pairs.size() / 2;
+    h->d_pairs.upload(pairs, st);
+    int nsm = 148;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
+    const long nchunk = (g.nloc + kTileK - 1) / kTileK;
+    long want = std::max<long>(1, (2L * nsm + 2L * h->npairs - 1) / (2L * h->npairs));  // ~2 waves of CTAs over both matrices
+    h->nsplit = (int)std::max<long>(1, std::min<long>(want, nchunk));
+    h->d_partial.alloc((size_t)2 * h->npairs * h->nsplit * kTileM * kTileN);
+
+    if (!h->h_P) CK(cudaMallocHost(&h->h_P, sizeof(double) * std::max<size_t>(1, (size_t)h->nbf * h->nbf)));
+    if (!h->h_res) CK(cudaMallocHost(&h->h_res, sizeof(double) * ((size_t)2 * h->nbf * h->nbf + 2)));
+
+    CK(cudaFuncSetAttribute(k_phi, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(((size_t)kPhiPts * (kPhiCols + 1) + (size_t)kPhiMaxExp * kPhiPts) * sizeof(double))));
+    CK(cudaFuncSetAttribute(k_rho, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRhoSmemBytes));
+    CK(cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConSmemBytes));
+    const size_t becke_smem = (size_t)kBeckeWarps * 2 * g.natoms * sizeof(double);
+    if (becke_smem > 200 * 1024) throw std::runtime_error("too many atoms for the Becke kernel's shared-memory layout");
+    CK(cudaFuncSetAttribute(k_becke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(becke_smem, 1024)));
+
+    // ---- kernels
+    record(h, 0);
+    if (g.nloc > 0) {
+        k_points<<<(unsigned)((g.nloc + 255) / 256), 256, 0, st>>>(g, h->d_atom_xyz.p, h->d_rtab.p, h->d_wrad.p, h->d_leb.p,
+                                                                  h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p);
+        h->launches++;
+    }
+    record(h, 1);
+    if (g.nloc > 0) {
+        k_becke<<<(unsigned)((g.nloc + kBeckeWarps - 1) / kBeckeWarps), kBeckeWarps * 32, becke_smem, st>>>(
+            g, h->d_atom_xyz.p, nullptr, h->d_Rdist.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p, h->d_wb.p);
+        h->launches++;
+    }
+    record(h, 2);
+    if (g.nloc > 0) {
+        PhiBasis B{h->nbf, h->nbp, h->d_bf_center.p, h->d_bf_prim_off.p, h->d_center_exp_off.p, h->d_exp_alpha.p,
+                   h->d_prim_exp.p, h->d_prim_coeff.p, h->d_prim_norm.p, h->d_prim_lmn.p, h->d_center_xyz.p};
+        const size_t smem = ((size_t)kPhiPts * (kPhiCols + 1) + (size_t)kPhiMaxExp * kPhiPts) * sizeof(double);
+        k_phi<<<(unsigned)((g.nloc + kPhiPts - 1) / kPhiPts), kPhiPts, smem, st>>>(g.nloc, B, h->d_x.p, h->d_y.p, h->d_z.p, h->d_phi.p);
+        h->launches++;
+    }
+    record(h, 3);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    h->t_ms[DFTGRID_T_POINTS] = elapsed(h, 0, 1);
+    h->t_ms[DFTGRID_T_BECKE] = elapsed(h, 1, 2);
+    h->t_ms[DFTGRID_T_PHI] = elapsed(h, 2, 3);
+    h->built = true;
+}
+
+// rho = 2 phi^T P phi, rescale to sum(Z), LDA pointwise, charge / E_xc sums
+void run_density(dftgrid* h) {
+    cudaStream_t st = h->stream;
+    const GridShape& g = h->g;
+    const long nshell = (long)g.natoms * g.nrad;
+    record(h, 4);
+    if (g.nloc > 0) {
+        k_rho<<<(unsigned)((g.nloc + kTileM - 1) / kTileM), kDenseThreads, kRhoSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_rho.p, g.nloc, h->nbp);
+        h->launches++;
+    }
+    record(h, 5);
+    const unsigned sblocks = (unsigned)((g.nshell_loc * 32 + 255) / 256);
+    if (h->nranks > 1) h->d_shell_raw.zero(st);
+    if (g.nloc > 0) {
+        k_shell_sum<<<sblocks, 256, 0, st>>>(g, h->d_w.p, h->d_rho.p, h->d_shell_raw.p, 1, 0);
+        h->launches++;
+    }
+    allreduce(h, h->d_shell_raw.p, (size_t)nshell);
+    k_totals<<<1, 256, 0, st>>>(g, h->d_shell_raw.p, 1, h->zsum, 0, h->d_qatom.p, h->d_scalars.p);
+    h->launches++;
+    if (h->nranks > 1) h->d_shell2.zero(st);
+    if (g.nloc > 0) {
+        k_scale_xc<<<(unsigned)((g.nloc + 255) / 256), 256, 0, st>>>(g.nloc, h->lda, h->d_scalars.p, h->d_w.p, h->d_rho.p, h->d_dxc.p, h->d_exw.p);
+        k_shell_sum<<<sblocks, 256, 0, st>>>(g, h->d_w.p, h->d_rho.p, h->d_shell2.p, 2, 0);
+        k_shell_sum<<<sblocks, 256, 0, st>>>(g, h->d_w.p, h->d_exw.p, h->d_shell2.p, 2, 1);
+        h->launches += 3;
+    }
+    record(h, 6);
+    // Ylm projection of the rescaled density; shares the collective with the shell sums
+    double* rho_lm = h->d_shell2.p + (size_t)nshell * 2;
+    if (g.nloc > 0) {
+        const int threads = round_up(g.nlm, 32);
+        k_rho_lm<<<(unsigned)g.nshell_loc, threads, 3 * g.nang * sizeof(double), st>>>(g, h->d_rho.p, h->d_wb.p, h->d_leb.p, h->d_Y.p, rho_lm);
+        h->launches++;
+    }
+    record(h, 7);
+    allreduce(h, h->d_shell2.p, (size_t)nshell * 2 + (size_t)nshell * g.nlm);
+    k_totals<<<1, 256, 0, st>>>(g, h->d_shell2.p, 2, h->zsum, 1, h->d_qatom.p, h->d_scalars.p);
+    h->launches++;
+    record(h, 8);
+    h->have_density = true;
+    h->have_potential = false;
+    h->contract_valid = false;
+    h->timed_iter = false;
+}
+
+// Hartree potential on every local point (rho_lm -> U_lm -> splines -> V)
+void run_potential(dftgrid* h) {
+    cudaStream_t st = h->stream;
+    const GridShape& g = h->g;
+    const long nshell = (long)g.natoms * g.nrad;
+    const long nsys = (long)g.natoms * g.nlm;
+    double* rho_lm = h->d_shell2.p + (size_t)nshell * 2;
+    record(h, 9);
+    k_poisson<<<(unsigned)((nsys + 63) / 64), 64, 0, st>>>(g, g.nrad + 2, h->d_lu.p, h->d_perm.p, h->d_lo.p, h->d_hi.p, h->d_rtab.p,
+                                                          rho_lm, h->d_qatom.p, h->d_work.p, h->d_U_lm.p);
+    k_spline<<<(unsigned)((nsys + 63) / 64), 64, 0, st>>>(g, h->spline, h->d_U_lm.p, h->d_work.p, h->d_coef.p);
+    h->launches += 2;
+    if (g.nloc > 0) {
+        k_v_own<<<(unsigned)g.nshell_loc, 128, g.nlm * sizeof(double), st>>>(g, h->d_rtab.p, h->d_leb.p, h->d_Yt.p, h->d_U_lm.p, h->d_Vown.p);
+        h->launches++;
+    }
+    record(h, 10);
+    if (g.nloc > 0) {
+        const size_t smem = ((size_t)g.nrad + (size_t)(g.lmax + 1) * (g.lmax + 1) + 2 * g.lmax + 2) * sizeof(double);
+        k_interp<<<(unsigned)((g.nloc + 127) / 128), 128, smem, st>>>(g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p, h->d_Vown.p,
+                                                                      h->d_xs.p, h->d_pre.p, h->d_coef.p, h->d_V.p, h->d_dJ.p);
+        h->launches++;
+    }
+    record(h, 11);
+    h->have_potential = true;
+}
+
+// [XC | J] = Phi^T diag(d) Phi, results laid out as res = [J (nb^2) | XC (nb^2) | exc | nel]
+void run_contract(dftgrid* h) {
+    cudaStream_t st = h->stream;
+    const GridShape& g = h->g;
+    const size_t nb2 = (size_t)h->nbf * h->nbf;
+    record(h, 12);
+    dim3 grid(h->npairs, h->nsplit, 2);
+    k_contract<<<grid, kDenseThreads, kConSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_pairs.p, h->d_partial.p, g.nloc, h->nbp, h->nsplit);
+    k_contract_reduce<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->npairs, h->nsplit, h->nbf, 1.0, 0.5,
+                                                         h->d_res.p + nb2, h->d_res.p);
+    h->launches += 2;
+    // exc and nel come from the already-reduced shell sums (identical on every rank): appended after the reduced block
+    CK(cudaMemcpyAsync(h->d_res.p + 2 * nb2, h->d_scalars.p + 2, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->d_res.p + 2 * nb2 + 1, h->d_scalars.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    record(h, 13);
+    allreduce(h, h->d_res.p, 2 * nb2);
+    record(h, 14);
+    h->contract_valid = h->have_potential;
+    h->timed_iter = h->have_potential;
+}
+
+__global__ void k_pad_P(const double* __restrict__ Praw, double* __restrict__ P, int nb, int nbp) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)nb * nb) return;
+    const int i = (int)(t / nb), j = (int)(t % nb);
+    P[(size_t)i * nbp + j] = Praw[t];
+}
+
+void upload_P(dftgrid* h, const double* P) {
+    if (!h->built) throw std::runtime_error("dftgrid_build has not been called");
+    const size_t nb2 = (size_t)h->nbf * h->nbf;
+    std::memcpy(h->h_P, P, nb2 * sizeof(double));
+    CK(cudaMemcpyAsync(h->d_Praw.p, h->h_P, nb2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // P is symmetric, so Eigen's column-major and our row-major padded copy coincide
+    k_pad_P<<<(unsigned)((nb2 + 255) / 256), 256, 0, h->stream>>>(h->d_Praw.p, h->d_P.p, h->nbf, h->nbp);
+    h->launches++;
+}
+
+void finish_timings(dftgrid* h) {
+    h->t_ms[DFTGRID_T_RHO] = elapsed(h, 4, 5);
+    h->t_ms[DFTGRID_T_XCPOINT] = elapsed(h, 5, 6) + elapsed(h, 7, 8);
+    h->t_ms[DFTGRID_T_RHOLM] = elapsed(h, 6, 7);
+    h->t_ms[DFTGRID_T_POISSON] = elapsed(h, 9, 10);
+    h->t_ms[DFTGRID_T_INTERP] = elapsed(h, 10, 11);
+    h->t_ms[DFTGRID_T_CONTRACT] = elapsed(h, 12, 13);
+    h->t_ms[DFTGRID_T_COMM] = elapsed(h, 13, 14);
+    h->t_ms[DFTGRID_T_TOTAL] = elapsed(h, 4, 14);
+}
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return 1;
+    } catch (...) {
+        g_error = "unknown error";
+        return 2;
+    }
+}
+
+void use_device(dftgrid* h) { CK(cudaSetDevice(h->device)); }
+
+template <typename T>
+void download(dftgrid* h, const DevBuf<T>& b, T* out, size_t count) {
+    use_device(h);
+    CK(cudaMemcpyAsync(out, b.p, count * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dftgrid_last_error(void) { return g_error.c_str(); }
+int dftgrid_abi_version(void) { return 1; }
+
+int dftgrid_create(dftgrid_t** out, const dftgrid_system* sys, const dftgrid_params* prm, int device, int rank, int nranks) {
+    return guarded([&] {
+        if (!out || !sys || !prm) throw std::runtime_error("null argument");
+        *out = nullptr;
+        if (sys->natoms <= 0 || sys->nbf <= 0 || sys->nprim <= 0) throw std::runtime_error("empty system");
+        if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("bad rank/nranks");
+        if (prm->radial_points < 6) throw std::runtime_error("radial_points must be at least 6");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw std::runtime_error(std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+        if (device < 0 || device >= ndev) throw std::runtime_error("bad CUDA device ordinal");
+        std::unique_ptr<dftgrid> h(new dftgrid());
+        h->device = device;
+        h->rank = rank;
+        h->nranks = nranks;
+        h->prm = *prm;
+        h->natoms = sys->natoms;
+        h->Z.assign(sys->Z, sys->Z + sys->natoms);
+        h->atom_xyz.assign(sys->xyz, sys->xyz + 3 * sys->natoms);
+        h->zsum = 0.0;
+        for (int a = 0; a < sys->natoms; a++) h->zsum += (double)sys->Z[a];  // charge += get_atomic_charge(i), src/moleculargrid.cpp:138
+        prepare_basis(h.get(), sys);
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw std::runtime_error("this library is built for sm_100a (B200) only");
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+        *out = h.release();
+    });
+}
+
+void dftgrid_destroy(dftgrid_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    delete h;
+}
+
+int dftgrid_comm_unique_id(void* id128) {
+    return guarded([&] {
+        if (!nccl_api().load()) throw std::runtime_error("cannot load libnccl.so.2");
+        NcclUniqueId id;
+        int rc = nccl_api().GetUniqueId(&id);
+        if (rc != 0) throw std::runtime_error(std::string("ncclGetUniqueId: ") + nccl_api().GetErrorString(rc));
+        std::memcpy(id128, &id, sizeof id);
+    });
+}
+
+int dftgrid_comm_init(dftgrid_t* h, const void* id128) {
+    return guarded([&] {
+        if (!nccl_api().load()) throw std::runtime_error("cannot load libnccl.so.2");
+        use_device(h);
+        NcclUniqueId id;
+        std::memcpy(&id, id128, sizeof id);
+        int rc = nccl_api().CommInitRank(&h->comm, h->nranks, id, h->rank);
+        if (rc != 0) throw std::runtime_error(std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(rc));
+    });
+}
+
+int dftgrid_build(dftgrid_t* h) {
+    return guarded([&] {
+        use_device(h);
+        do_build(h);
+    });
+}
+
+long dftgrid_npoints(const dftgrid_t* h) { return h->g.npts; }
+long dftgrid_npoints_local(const dftgrid_t* h) { return h->g.nloc; }
+long dftgrid_point_offset(const dftgrid_t* h) { return h->g.shell0 * h->g.nang; }
+int dftgrid_nbf(const dftgrid_t* h) { return h->nbf; }
+int dftgrid_nlm(const dftgrid_t* h) { return h->g.nlm; }
+
+int dftgrid_upload_density(dftgrid_t* h, const double* P) {
+    return guarded([&] {
+        use_device(h);
+        upload_P(h, P);
+    });
+}
+
+int dftgrid_set_density(dftgrid_t* h, const double* P) {
+    return guarded([&] {
+        use_device(h);
+        upload_P(h, P);
+        run_density(h);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dftgrid_hartree_J(dftgrid_t* h, double* J) {
+    return guarded([&] {
+        use_device(h);
+        if (!h->have_density) throw std::runtime_error("dftgrid_set_density has not been called");
+        const size_t nb2 = (size_t)h->nbf * h->nbf;
+        run_potential(h);
+        run_contract(h);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_res, h->d_res.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        std::memcpy(J, h->h_res, nb2 * sizeof(double));
+    });
+}
+
+int dftgrid_xc(dftgrid_t* h, double* XC, double* exc) {
+    return guarded([&] {
+        use_device(h);
+        if (!h->have_density) throw std::runtime_error("dftgrid_set_density has not been called");
+        const size_t nb2 = (size_t)h->nbf * h->nbf;
+        if (!h->contract_valid) {
+            // XC asked for before J: the J half of the fused contraction still needs a defined weight vector
+            if (!h->have_potential) h->d_dJ.zero(h->stream);
+            run_contract(h);
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_res, h->d_res.p + nb2, (nb2 + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (XC) std::memcpy(XC, h->h_res, nb2 * sizeof(double));
+        if (exc) *exc = h->h_res[nb2];
+    });
+}
+
+int dftgrid_electron_count(dftgrid_t* h, double* nelec) {
+    return guarded([&] {
+        use_device(h);
+        if (!h->have_density) throw std::runtime_error("dftgrid_set_density has not been called");
+        CK(cudaMemcpyAsync(h->h_res, h->d_scalars.p + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        *nelec = h->h_res[0];
+    });
+}
+
+int dftgrid_iteration_device(dftgrid_t* h) {
+    return guarded([&] {
+        use_device(h);
+        if (!h->built) throw std::runtime_error("dftgrid_build has not been called");
+        run_density(h);
+        run_potential(h);
+        run_contract(h);
+        CK(cudaGetLastError());
+    });
+}
+
+int dftgrid_download_results(dftgrid_t* h, double* J, double* XC, double* exc, double* nelec) {
+    return guarded([&] {
+        use_device(h);
+        const size_t nb2 = (size_t)h->nbf * h->nbf;
+        CK(cudaMemcpyAsync(h->h_res, h->d_res.p, (2 * nb2 + 2) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (J) std::memcpy(J, h->h_res, nb2 * sizeof(double));
+        if (XC) std::memcpy(XC, h->h_res + nb2, nb2 * sizeof(double));
+        if (exc) *exc = h->h_res[2 * nb2];
+        if (nelec) *nelec = h->h_res[2 * nb2 + 1];
+    });
+}
+
+int dftgrid_iteration(dftgrid_t* h, const double* P, double* J, double* XC, double* exc, double* nelec) {
+    int rc = dftgrid_upload_density(h, P);
+    if (rc) return rc;
+    rc = dftgrid_iteration_device(h);
+    if (rc) return rc;
+    return dftgrid_download_results(h, J, XC, exc, nelec);
+}
+
+int dftgrid_synchronize(dftgrid_t* h) {
+    return guarded([&] {
+        use_device(h);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+    });
+}
+
+int dftgrid_get_positions(dftgrid_t* h, double* xyz) {
+    return guarded([&] {
+        const size_t n = (size_t)h->g.nloc;
+        std::vector<double> x(n), y(n), z(n);
+        download(h, h->d_x, x.data(), n);
+        download(h, h->d_y, y.data(), n);
+        download(h, h->d_z, z.data(), n);
+        for (size_t i = 0; i < n; i++) {
+            xyz[3 * i] = x[i];
+            xyz[3 * i + 1] = y[i];
+            xyz[3 * i + 2] = z[i];
+        }
+    });
+}
+int dftgrid_get_weights(dftgrid_t* h, double* w) { return guarded([&] { download(h, h->d_w, w, (size_t)h->g.nloc); }); }
+int dftgrid_get_becke_weights(dftgrid_t* h, double* wb) { return guarded([&] { download(h, h->d_wb, wb, (size_t)h->g.nloc); }); }
+int dftgrid_get_densities(dftgrid_t* h, double* rho) { return guarded([&] { download(h, h->d_rho, rho, (size_t)h->g.nloc); }); }
+int dftgrid_get_potential(dftgrid_t* h, double* V) { return guarded([&] { download(h, h->d_V, V, (size_t)h->g.nloc); }); }
+int dftgrid_get_amplitudes(dftgrid_t* h, double* phi) {
+    return guarded([&] {
+        use_device(h);
+        const size_t n = (size_t)h->g.nloc;
+        CK(cudaMemcpy2DAsync(phi, (size_t)h->nbf * sizeof(double), h->d_phi.p, (size_t)h->nbp * sizeof(double),
+                             (size_t)h->nbf * sizeof(double), n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    });
+}
+int dftgrid_get_rho_lm(dftgrid_t* h, double* out) {
+    return guarded([&] {
+        use_device(h);
+        const size_t nshell = (size_t)h->g.natoms * h->g.nrad;
+        CK(cudaMemcpyAsync(out, h->d_shell2.p + nshell * 2, nshell * h->g.nlm * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    });
+}
+int dftgrid_get_U_lm(dftgrid_t* h, double* out) {
+    return guarded([&] { download(h, h->d_U_lm, out, (size_t)h->g.natoms * h->g.nrad * h->g.nlm); });
+}
+
+int dftgrid_last_timings(dftgrid_t* h, double* out, int n) {
+    return guarded([&] {
+        use_device(h);
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->timed_iter) finish_timings(h);
+        for (int i = 0; i < n && i < DFTGRID_T_COUNT; i++) out[i] = h->t_ms[i];
+    });
+}
+
+long dftgrid_launch_count(const dftgrid_t* h) { return h->launches; }
+
+}  // extern "C"

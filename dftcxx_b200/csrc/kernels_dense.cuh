@@ -1,0 +1,307 @@
+// Dense FP64 contractions on the tensor pipe (DMMA, mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4 on sm_100a;
+// tcgen05/wgmma have no f64 kind, so warp-level DMMA fed from cp.async-staged shared memory is the
+// Blackwell FP64 tensor path).  Measured register-resident peak on this pool's B200: 37.05 TFLOP/s
+// (profiles/r01_fp64_peak_microbench.txt), identical to the DFMA peak, at a quarter of the issue slots.
+//
+//   k_rho      : rho_p = 2 * sum_n Phi[p][n] * (sum_k Phi[p][k] P[k][n])   (src/gridpoint.cpp:82-84)
+//   k_contract : C_z[i][j] = sum_p Phi[p][i] d_z[p] Phi[p][j], z in {XC, J} (src/dft.cpp:424-432, src/atomicgrid.cpp:471-488)
+//   k_contract_reduce : fixed-order sum of the split-K partials, mirrored into both triangles.
+//
+// Shared-memory tiles are padded so that every fragment load is bank-conflict free:
+//   [rows][32+4] doubles for "row = lane/4, col = lane%4" accesses, [rows][128+8] for "row = lane%4, col = lane/4".
+#pragma once
+#include "common.cuh"
+
+namespace dfg {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;  // src-size 0 => 16 zero bytes are written
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+constexpr int kDenseThreads = 256;  // 8 warps: 4 along M x 2 along N
+constexpr int kTileM = 128;
+constexpr int kTileN = 128;
+constexpr int kTileK = 32;
+constexpr int kLdK = kTileK + 4;    // 36
+constexpr int kLdN = kTileN + 8;    // 136
+constexpr int kStages = 3;
+
+// =========================================================================================================
+// rho
+// =========================================================================================================
+constexpr int kRhoStageDoubles = kTileM * kLdK + kTileK * kLdN;
+constexpr size_t kRhoSmemBytes = (size_t)kStages * kRhoStageDoubles * sizeof(double) + 2 * kTileM * sizeof(double);
+
+__device__ __forceinline__ void rho_load_stage(double* st, const double* __restrict__ phi, const double* __restrict__ P,
+                                               long p0, long nloc, int nbp, int slab, int kc) {
+    double* As = st;                      // [128][36]   Phi[p0+r][kc + c]
+    double* Bs = st + kTileM * kLdK;      // [32][136]   P[kc + r][slab + c]
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int ch = tid + it * kDenseThreads;  // 0..2047
+        const int r = ch >> 4, c = (ch & 15) * 2;
+        const long p = p0 + r;
+        const bool ok = p < nloc;
+        cp_async16(As + r * kLdK + c, phi + (ok ? p : 0) * (long)nbp + kc + c, ok);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int ch = tid + it * kDenseThreads;
+        const int r = ch >> 6, c = (ch & 63) * 2;
+        const bool ok = slab + c < nbp;
+        cp_async16(Bs + r * kLdN + c, P + (long)(kc + r) * nbp + (ok ? slab + c : 0), ok);
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void rho_mma_stage(const double* st, double (&acc)[4][8][2], int wm, int wn, int lane) {
+    const double* As = st;
+    const double* Bs = st + kTileM * kLdK;
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < kTileK; kk += 4) {
+        double a[4], b[NT];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) a[mt] = As[(wm * 32 + mt * 8 + g) * kLdK + kk + q];
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) b[nt] = Bs[(kk + q) * kLdN + wn * (NT * 8) + nt * 8 + g];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+}
+
+// grid.x = ceil(nloc/128); P is the zero-padded [nbp][nbp] density matrix (symmetric).
+__global__ void __launch_bounds__(kDenseThreads, 1)
+k_rho(const double* __restrict__ phi, const double* __restrict__ P, double* __restrict__ rho, long nloc, int nbp) {
+    extern __shared__ __align__(16) double sm[];
+    double* red = sm + (size_t)kStages * kRhoStageDoubles;  // [2][128]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, q = lane & 3;
+    const long p0 = (long)blockIdx.x * kTileM;
+    const int nk = nbp / kTileK;
+    const int nslab = (nbp + kTileN - 1) / kTileN;
+    const int total = nslab * nk;
+
+    double rowsum[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[4][8][2];
+
+    // prologue
+    for (int s = 0; s < kStages - 1; s++) {
+        if (s < total) rho_load_stage(sm + (size_t)s * kRhoStageDoubles, phi, P, p0, nloc, nbp, (s / nk) * kTileN, (s % nk) * kTileK);
+        cp_async_commit();
+    }
+    for (int it = 0; it < total; it++) {
+        const int slab = (it / nk) * kTileN, kci = it % nk;
+        const int ncols = min(kTileN, nbp - slab);  // 32, 64, 96 or 128
+        const bool narrow = ncols <= 64;            // 8 warps as 4 x 2 over [128 x 64]: 4 n-tiles per warp
+        if (kci == 0) {
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        }
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        {
+            const int nx = it + kStages - 1;
+            if (nx < total)
+                rho_load_stage(sm + (size_t)(nx % kStages) * kRhoStageDoubles, phi, P, p0, nloc, nbp, (nx / nk) * kTileN, (nx % nk) * kTileK);
+            cp_async_commit();
+        }
+        const double* st = sm + (size_t)(it % kStages) * kRhoStageDoubles;
+        if (narrow)
+            rho_mma_stage<4>(st, acc, wm, wn, lane);
+        else
+            rho_mma_stage<8>(st, acc, wm, wn, lane);
+        if (kci == nk - 1) {
+            // epilogue of this column slab: rowsum += T[p][n] * Phi[p][n]
+            const int ntn = narrow ? 4 : 8;
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+                const long p = p0 + wm * 32 + mt * 8 + g;
+                if (p < nloc) {
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        if (nt < ntn) {
+                            const int col = slab + wn * (ntn * 8) + nt * 8 + q * 2;
+                            if (col < nbp) {
+                                const double2 f = *reinterpret_cast<const double2*>(phi + p * (long)nbp + col);
+                                rowsum[mt] = fma(acc[mt][nt][0], f.x, rowsum[mt]);
+                                rowsum[mt] = fma(acc[mt][nt][1], f.y, rowsum[mt]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    // reduce over the 4 lanes of a quad, then over the two N-warps
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+        double v = rowsum[mt];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (q == 0) red[wn * kTileM + wm * 32 + mt * 8 + g] = v;
+    }
+    __syncthreads();
+    if (tid < kTileM) {
+        const long p = p0 + tid;
+        if (p < nloc) rho[p] = 2.0 * (red[tid] + red[kTileM + tid]);
+    }
+}
+
+// =========================================================================================================
+// C_z = Phi^T diag(d_z) Phi  (upper-triangular 128x128 tile pairs, split over point ranges)
+// =========================================================================================================
+constexpr int kConStageDoubles = 2 * kTileK * kLdN + kTileK;
+constexpr size_t kConSmemBytes = (size_t)kStages * kConStageDoubles * sizeof(double);
+
+__device__ __forceinline__ void con_load_stage(double* st, const double* __restrict__ phi, const double* __restrict__ d,
+                                               long pk, long pend, int nbp, int ci, int cj, bool diag) {
+    double* As = st;                     // [32][136]  Phi[pk+r][ci + c]
+    double* Bs = st + kTileK * kLdN;     // [32][136]  Phi[pk+r][cj + c]
+    double* ds = st + 2 * kTileK * kLdN; // [32]
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int ch = tid + it * kDenseThreads;
+        const int r = ch >> 6, c = (ch & 63) * 2;
+        const long p = pk + r;
+        const bool okp = p < pend;
+        const bool oki = okp && (ci + c < nbp);
+        cp_async16(As + r * kLdN + c, phi + (okp ? p : 0) * (long)nbp + (oki ? ci + c : 0), oki);
+        if (!diag) {
+            const bool okj = okp && (cj + c < nbp);
+            cp_async16(Bs + r * kLdN + c, phi + (okp ? p : 0) * (long)nbp + (okj ? cj + c : 0), okj);
+        }
+    }
+    if (tid < kTileK / 2) {
+        const long p = pk + tid * 2;
+        // d is padded to an even length and zero beyond the shard, so a 16-byte copy is always in bounds
+        cp_async16(ds + tid * 2, d + (p < pend ? p : 0), p < pend);
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void con_mma_stage(const double* st, bool diag, double (&acc)[4][8][2], int wm, int wn, int lane) {
+    const double* As = st;
+    const double* Bs = diag ? st : st + kTileK * kLdN;
+    const double* ds = st + 2 * kTileK * kLdN;
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < kTileK; kk += 4) {
+        double a[4], b[NT];
+        const double dv = ds[kk + q];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) a[mt] = As[(kk + q) * kLdN + wm * 32 + mt * 8 + g] * dv;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) b[nt] = Bs[(kk + q) * kLdN + wn * (NT * 8) + nt * 8 + g];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+}
+
+// grid = (npairs, nsplit, 2).  pair_ij[2*pair] = (ti, tj) with ti <= tj.  d0/d1: per-point weights of matrix 0/1
+// (the odd point of a half-filled last chunk is covered by zero padding of d).  partial: [2][npairs][nsplit][128*128].
+__global__ void __launch_bounds__(kDenseThreads, 1)
+k_contract(const double* __restrict__ phi, const double* __restrict__ d0, const double* __restrict__ d1,
+           const int* __restrict__ pair_ij, double* __restrict__ partial, long nloc, int nbp, int nsplit) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, q = lane & 3;
+    const int pair = blockIdx.x, split = blockIdx.y, z = blockIdx.z;
+    const int ti = pair_ij[2 * pair], tj = pair_ij[2 * pair + 1];
+    const int ci = ti * kTileM, cj = tj * kTileN;
+    const bool diag = ti == tj;
+    const double* d = z == 0 ? d0 : d1;
+    const long nchunk = (nloc + kTileK - 1) / kTileK;
+    const long c_begin = nchunk * split / nsplit, c_end = nchunk * (split + 1) / nsplit;
+    const int total = (int)(c_end - c_begin);
+    const int ncols = min(kTileN, nbp - cj);
+    const bool narrow = ncols <= 64;
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    for (int s = 0; s < kStages - 1; s++) {
+        if (s < total) con_load_stage(sm + (size_t)s * kConStageDoubles, phi, d, (c_begin + s) * kTileK, nloc, nbp, ci, cj, diag);
+        cp_async_commit();
+    }
+    for (int it = 0; it < total; it++) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        {
+            const int nx = it + kStages - 1;
+            if (nx < total)
+                con_load_stage(sm + (size_t)(nx % kStages) * kConStageDoubles, phi, d, (c_begin + nx) * kTileK, nloc, nbp, ci, cj, diag);
+            cp_async_commit();
+        }
+        const double* st = sm + (size_t)(it % kStages) * kConStageDoubles;
+        if (narrow)
+            con_mma_stage<4>(st, diag, acc, wm, wn, lane);
+        else
+            con_mma_stage<8>(st, diag, acc, wm, wn, lane);
+    }
+    cp_async_wait<0>();
+    double* out = partial + (((size_t)z * gridDim.x + pair) * nsplit + split) * (size_t)(kTileM * kTileN);
+    const int ntn = narrow ? 4 : 8;
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const int r = wm * 32 + mt * 8 + g;
+            if (nt < ntn) {
+                const int c = wn * (ntn * 8) + nt * 8 + q * 2;
+                *reinterpret_cast<double2*>(out + r * kTileN + c) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            } else if (narrow) {
+                const int c = 64 + wn * 32 + (nt - 4) * 8 + q * 2;
+                *reinterpret_cast<double2*>(out + r * kTileN + c) = make_double2(0.0, 0.0);
+            }
+        }
+}
+
+// out0/out1: nb x nb (symmetric => row/column-major agnostic).  Each thread sums one element over the splits in order.
+__global__ void k_contract_reduce(const double* __restrict__ partial, const int* __restrict__ pair_ij, int npairs, int nsplit,
+                                  int nb, double scale0, double scale1, double* __restrict__ out0, double* __restrict__ out1) {
+    const int pair = blockIdx.x, z = blockIdx.y;
+    const int ti = pair_ij[2 * pair], tj = pair_ij[2 * pair + 1];
+    const double* base = partial + ((size_t)z * npairs + pair) * nsplit * (size_t)(kTileM * kTileN);
+    double* out = z == 0 ? out0 : out1;
+    const double scale = z == 0 ? scale0 : scale1;
+    for (int e = threadIdx.x; e < kTileM * kTileN; e += blockDim.x) {
+        const int r = e / kTileN, c = e % kTileN;
+        const int gi = ti * kTileM + r, gj = tj * kTileN + c;
+        if (gi >= nb || gj >= nb) continue;
+        if (ti == tj && gj < gi) continue;  // lower part of a diagonal tile is the mirror image
+        double s = 0.0;
+        for (int k = 0; k < nsplit; k++) s += base[(size_t)k * (kTileM * kTileN) + e];
+        s *= scale;
+        out[(size_t)gi * nb + gj] = s;
+        out[(size_t)gj * nb + gi] = s;
+    }
+}
+
+}  // namespace dfg

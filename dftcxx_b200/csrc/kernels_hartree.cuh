@@ -1,0 +1,350 @@
+// Pointwise LDA, charge sums and the Becke/Poisson Hartree potential kernels.
+#pragma once
+#include "common.cuh"
+#include "host_tables.h"
+
+namespace dfg {
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-shell sums  out[gshell*stride + slot] = sum_a w*v  (warp per local shell, fixed reduction order).
+// Used for sum(w rho) (src/atomicgrid.cpp:520-530).
+__global__ void k_shell_sum(GridShape g, const double* __restrict__ w, const double* __restrict__ v,
+                            double* __restrict__ out, int stride, int slot) {
+    const long s = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= g.nshell_loc) return;
+    double acc = 0.0;
+    for (int a = lane; a < g.nang; a += 32) acc = fma(w[s * g.nang + a], v[s * g.nang + a], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(g.shell0 + s) * stride + slot] = acc;
+}
+
+// Single-block bookkeeping: per-atom charges q_atom = sum over the atom's shells (radial order), total, and
+// (mode 0) the rescale factor sum(Z)/sum(w rho) of MolecularGrid::correct_densities (src/moleculargrid.cpp:132-146),
+// or (mode 1) electron count + E_xc written to results[0..1].
+__global__ void k_totals(GridShape g, const double* __restrict__ shellsum, int stride, double zsum, int mode,
+                         double* __restrict__ q_atom, double* __restrict__ scalars /*[0]=scale [1]=nel [2]=exc*/) {
+    __shared__ double part[256];
+    for (int a = threadIdx.x; a < g.natoms; a += blockDim.x) {
+        double q = 0.0;
+        for (int i = 0; i < g.nrad; i++) q += shellsum[((long)a * g.nrad + i) * stride + 0];
+        q_atom[a] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int a = 0; a < g.natoms; a++) tot += q_atom[a];
+        if (mode == 0) scalars[0] = zsum / tot;
+        if (mode == 1) scalars[1] = tot;
+    }
+    if (mode == 1) {
+        // E_xc = sum over shells of the per-shell sums (fixed order: strided partials, then tree)
+        double e = 0.0;
+        const long ns = (long)g.natoms * g.nrad;
+        for (long s = threadIdx.x; s < ns; s += blockDim.x) e += shellsum[s * stride + 1];
+        part[threadIdx.x] = e;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) scalars[2] = part[0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// rho *= scale, then Slater-Xalpha exchange + VWN5 correlation for a closed shell (rho_a = rho_b = rho/2):
+// src/functionals.cpp:24-63 (exchange), 65-114 with zeta = 0 => g = 0 < tol, paramagnetic branch only, 116-150.
+//   dxc[p] = w * ((vxa+vxb+vca+vcb) * 0.5)      (src/dft.cpp:424)
+//   exw[p] = ex + ec                             (E_xc = sum w*(ex+ec), src/dft.cpp:417)
+__device__ __forceinline__ double vwn_X(double x, double b, double c) { return x * x + b * x + c; }
+
+__global__ void k_scale_xc(long nloc, LdaConstants K, const double* __restrict__ scalars, const double* __restrict__ w,
+                           double* __restrict__ rho, double* __restrict__ dxc, double* __restrict__ exw) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nloc) return;
+    const double r = rho[p] * scalars[0];
+    rho[p] = r;
+    const double ra = r * 0.5;
+    double ex = 0.0, vxa = 0.0;
+    if (!(ra < 1e-10)) {
+        const double rho3 = pow(ra, 1.0 / 3.0);
+        const double t = K.fac * ra * rho3;
+        ex = t + t;
+        vxa = K.vfac * rho3;
+    }
+    double ec = 0.0, vca = 0.0;
+    const double dens = ra + ra;
+    if (!(dens < 1e-10)) {
+        const double x = pow(K.x_pref / dens, 1.0 / 6.0);
+        const double Xx = vwn_X(x, K.b, K.c);
+        const double twoxb = 2.0 * x + K.b;
+        const double epsp = K.a * (log(x * x / Xx) - K.bx0_over_Xx0 * log((x - K.x0) * (x - K.x0) / Xx) + K.atan_pref * atan(K.q / twoxb));
+        const double den2 = twoxb * twoxb + K.q * K.q;
+        const double depsp = K.a * (2.0 / x - twoxb / Xx - 4.0 * K.b / den2 -
+                                    (K.b * K.x0 / K.Xx0) * (2.0 / (x - K.x0) - twoxb / Xx - 4.0 * (2.0 * K.x0 + K.b) / den2));
+        ec = epsp * dens;
+        vca = epsp - (x / 6.0) * depsp;
+    }
+    dxc[p] = w[p] * ((vxa + vxa + vca + vca) * 0.5);
+    exw[p] = ex + ec;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// rho_lm(i, lm) = 4 pi sum_j rho(i,j) * Y_lm(j) * w_leb(j) * w_becke(i,j)   (src/atomicgrid.cpp:258-295)
+// Block per local shell, thread per lm; j runs in the reference's order.
+__global__ void k_rho_lm(GridShape g, const double* __restrict__ rho, const double* __restrict__ wb,
+                         const double* __restrict__ leb, const double* __restrict__ Y /*[nang][nlm]*/,
+                         double* __restrict__ rho_lm /*[natoms*nrad][nlm]*/) {
+    extern __shared__ double sm[];
+    double* rs = sm;               // rho
+    double* ws = sm + g.nang;      // lebedev weight
+    double* bs = sm + 2 * g.nang;  // becke weight
+    const long s = blockIdx.x;
+    for (int j = threadIdx.x; j < g.nang; j += blockDim.x) {
+        rs[j] = rho[s * g.nang + j];
+        ws[j] = leb[4 * j + 3];
+        bs[j] = wb[s * g.nang + j];
+    }
+    __syncthreads();
+    const int lm = threadIdx.x;
+    if (lm >= g.nlm) return;
+    double acc = 0.0;
+    for (int j = 0; j < g.nang; j++) acc += rs[j] * Y[(long)j * g.nlm + lm] * ws[j] * bs[j];
+    rho_lm[(g.shell0 + s) * g.nlm + lm] = acc * (4.0 * 3.14159265358979323846);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Radial Poisson solve for every (atom, lm): M_l U = g with the pre-factorised operators (host_tables.h),
+// g_0 = sqrt(4 pi) q_atom for lm = 0 else 0, g_i = -4 pi r_i rho_lm(i), g_{N+1} = 0  (src/atomicgrid.cpp:395-432).
+// Thread per system, atom fastest so a warp shares l (the LU entries are then warp-uniform broadcasts).
+// work: [(N+2)][nsys] scratch.
+__global__ void k_poisson(GridShape g, int n /*N+2*/, const double* __restrict__ lu, const int* __restrict__ perm,
+                          const int* __restrict__ lo, const int* __restrict__ hi, const double* __restrict__ r_tab,
+                          const double* __restrict__ rho_lm, const double* __restrict__ q_atom,
+                          double* __restrict__ work, double* __restrict__ U_lm /*[natoms*nrad][nlm]*/) {
+    const long nsys = (long)g.natoms * g.nlm;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsys) return;
+    const int atom = (int)(t % g.natoms), lm = (int)(t / g.natoms);
+    int l = 0;
+    while ((l + 1) * (l + 1) <= lm) l++;
+    const double* M = lu + (size_t)l * n * n;
+    const int* pr = perm + (size_t)l * n;
+    const int* lor = lo + (size_t)l * n;
+    const int* hir = hi + (size_t)l * n;
+    const int N = n - 2;
+    const double sqrt4pi = 3.5449077018110318;  // sqrt(4*M_PI)
+    auto rhs = [&](int i) -> double {
+        if (i == 0) return lm == 0 ? sqrt4pi * q_atom[atom] : 0.0;
+        if (i == N + 1) return 0.0;
+        return -4.0 * 3.14159265358979323846 * r_tab[i - 1] * rho_lm[((long)atom * g.nrad + (i - 1)) * g.nlm + lm];
+    };
+    double* x = work + t;  // stride nsys
+    for (int i = 0; i < n; i++) {  // L y = P g
+        double acc = rhs(pr[i]);
+        for (int j = lor[i]; j < i; j++) acc -= M[(size_t)i * n + j] * x[(size_t)j * nsys];
+        x[(size_t)i * nsys] = acc;
+    }
+    for (int i = n - 1; i >= 0; i--) {  // U x = y
+        double acc = x[(size_t)i * nsys];
+        for (int j = hir[i]; j > i; j--) acc -= M[(size_t)i * n + j] * x[(size_t)j * nsys];
+        x[(size_t)i * nsys] = acc / M[(size_t)i * n + i];
+    }
+    for (int i = 1; i < N + 1; i++) U_lm[((long)atom * g.nrad + (i - 1)) * g.nlm + lm] = x[(size_t)i * nsys];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Not-a-knot cubic splines through (r ascending, U_lm) for every (atom, lm): Cspline::generate_spline
+// (src/cspline.cpp:66-142) with the x-only part of the tridiagonal sweep precomputed on the host.
+// Output table coef[atom][interval][lm][4] (a,b,c,d); interval N-1 is the clamp y.back() (src/cspline.cpp:159-161).
+struct SplineDev {
+    const double* x;    // [N]
+    const double* A;    // [N]
+    const double* Cp;   // [N]
+    const double* den;  // [N]
+    const double* h;    // [N]
+    const double* rh;   // [N]
+    double fw0, fh0, lh1, lw1;
+};
+
+__global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_lm, double* __restrict__ work /*[2][N][nsys]*/,
+                         double* __restrict__ coef) {
+    const long nsys = (long)g.natoms * g.nlm;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsys) return;
+    const int lm = (int)(t % g.nlm), atom = (int)(t / g.nlm);
+    const int N = g.nrad;
+    auto y = [&](int i) -> double { return U_lm[((long)atom * N + (N - 1 - i)) * g.nlm + lm]; };  // ascending r
+    double* Y = work + t;                        // stride nsys
+    double* D = work + (size_t)N * nsys + t;     // stride nsys
+    // right-hand sides (src/cspline.cpp:81-109)
+    {
+        const double r0 = (y(1) - y(0)) / S.h[0], r1 = (y(2) - y(1)) / S.h[1];
+        Y[0] = r0 * S.fw0 + r1 * S.fh0 * S.fh0;
+    }
+    double r0 = 0.0, r1 = 0.0;
+    for (int i = 1; i < N - 1; i++) {
+        r0 = (y(i) - y(i - 1)) / S.h[i - 1];
+        r1 = (y(i + 1) - y(i)) / S.h[i];
+        Y[(size_t)i * nsys] = 3 * (r0 * S.h[i] + r1 * S.h[i - 1]);
+    }
+    Y[(size_t)(N - 1) * nsys] = r0 * S.lh1 * S.lh1 + r1 * S.lw1;
+    // forward sweep and back substitution (src/cspline.cpp:111-127)
+    Y[0] = Y[0] / S.den[0];
+    for (int i = 1; i < N; i++) Y[(size_t)i * nsys] = (Y[(size_t)i * nsys] - S.A[i] * Y[(size_t)(i - 1) * nsys]) / S.den[i];
+    D[(size_t)(N - 1) * nsys] = Y[(size_t)(N - 1) * nsys];
+    for (int i = N - 1; i > 0; i--) D[(size_t)(i - 1) * nsys] = Y[(size_t)(i - 1) * nsys] - S.Cp[i - 1] * D[(size_t)i * nsys];
+    // polynomial coefficients (src/cspline.cpp:130-139)
+    for (int i = 0; i < N - 1; i++) {
+        const double dx = S.rh[i];
+        const double dy = (y(i + 1) - y(i)) * dx;
+        const double Di = D[(size_t)i * nsys], Dn = D[(size_t)(i + 1) * nsys];
+        double4 c;
+        c.x = y(i);
+        c.y = Di;
+        c.z = dx * (3 * dy - 2 * Di - Dn);
+        c.w = dx * dx * (-2 * dy + Di + Dn);
+        *reinterpret_cast<double4*>(coef + (((size_t)atom * N + i) * g.nlm + lm) * 4) = c;
+    }
+    *reinterpret_cast<double4*>(coef + (((size_t)atom * N + (N - 1)) * g.nlm + lm) * 4) = make_double4(y(N - 1), 0.0, 0.0, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Own-cell potential V_fuzzy(p) = sum_lm (1/r) * Y_lm(p) * U_lm(i)  (src/atomicgrid.cpp:437-462).
+// Block per local shell; Yt is the transposed table [nlm][nang].
+__global__ void k_v_own(GridShape g, const double* __restrict__ r_tab, const double* __restrict__ leb,
+                        const double* __restrict__ Yt, const double* __restrict__ U_lm, double* __restrict__ Vown) {
+    extern __shared__ double sm[];
+    const long s = blockIdx.x;
+    const long gs = g.shell0 + s;
+    const int i = (int)(gs % g.nrad);
+    for (int lm = threadIdx.x; lm < g.nlm; lm += blockDim.x) sm[lm] = U_lm[gs * g.nlm + lm];
+    __syncthreads();
+    const double r = r_tab[i];
+    for (int j = threadIdx.x; j < g.nang; j += blockDim.x) {
+        const double qx = __dmul_rn(leb[4 * j], r), qy = __dmul_rn(leb[4 * j + 1], r), qz = __dmul_rn(leb[4 * j + 2], r);
+        const double rr = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)), __dmul_rn(qz, qz)));
+        const double rinv = 1.0 / rr;
+        double v = 0.0;
+        for (int lm = 0; lm < g.nlm; lm++) v += rinv * Yt[(long)lm * g.nang + j] * sm[lm];
+        Vown[s * g.nang + j] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Cross-atom interpolation (src/moleculargrid.cpp:342-380): for point p of atom i
+//   V(p) = sum_k [ k == i ? V_fuzzy(p) : sum_lm (1/r) pre_lm P_l^|m|(cos th) {cos m ph | sin |m| ph} S_{k,lm}(r) ]
+// with r, th, ph the spherical coordinates of p - R_k and S the clamped cubic spline (src/cspline.cpp:151-172).
+// Thread per point, atoms k in ascending order.  Y_lm is generated once per (p,k) by the reference's own
+// Legendre recurrences (src/spherical_harmonics.cpp:81-117) run column-wise in m, and cos/sin(m ph) by the
+// angle-addition recurrence from cos ph = x/rho_xy, sin ph = y/rho_xy (atan2(0,0) = 0 => cos = 1, sin = 0).
+// The radial interval is found by bisection on the shared abscissa.  dJ[p] = w[p]*V[p] feeds the J contraction.
+constexpr int kMaxL = 15;
+
+__global__ void __launch_bounds__(128)
+k_interp(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ px, const double* __restrict__ py,
+         const double* __restrict__ pz, const double* __restrict__ w, const double* __restrict__ Vown,
+         const double* __restrict__ xs /*[N] ascending*/, const double* __restrict__ pre /*[(lmax+1)^2]*/,
+         const double* __restrict__ coef, double* __restrict__ V, double* __restrict__ dJ) {
+    extern __shared__ double sm[];
+    const int N = g.nrad, L = g.lmax;
+    double* xsh = sm;            // [N]
+    double* presh = sm + N;      // [(L+1)^2]
+    double* rj = presh + (L + 1) * (L + 1);  // [2L+2] reciprocals 1/(j-m)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) xsh[i] = xs[i];
+    for (int i = threadIdx.x; i < (L + 1) * (L + 1); i += blockDim.x) presh[i] = pre[i];
+    for (int i = threadIdx.x; i < 2 * L + 2; i += blockDim.x) rj[i] = i > 0 ? 1.0 / (double)i : 0.0;
+    __syncthreads();
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.nloc) return;
+    const int own = (int)((g.shell0 + p / g.nang) / g.nrad);
+    const double x = px[p], y = py[p], z = pz[p];
+    double Vacc = 0.0;
+    for (int k = 0; k < g.natoms; k++) {
+        if (k == own) {
+            Vacc += Vown[p];
+            continue;
+        }
+        const double dx = x - atom_xyz[3 * k], dy = y - atom_xyz[3 * k + 1], dz = z - atom_xyz[3 * k + 2];
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);
+        const double rinv = 1.0 / r;
+        // spline interval: r < x0 -> (0, t=0); r >= x_last -> (N-1, t=0); else first i with r <= x_i -> (i-1, r - x_{i-1})
+        int iv;
+        double tt;
+        if (r < xsh[0]) {
+            iv = 0;
+            tt = 0.0;
+        } else if (r >= xsh[N - 1]) {
+            iv = N - 1;
+            tt = 0.0;
+        } else {
+            int lo_ = 0, hi_ = N - 1;  // invariant: x[lo_] < r <= x[hi_]  (r == x[0] handled: first i with r <= x_i is 1)
+            if (r == xsh[0]) {
+                hi_ = 1;
+            } else {
+                while (hi_ - lo_ > 1) {
+                    const int mid = (lo_ + hi_) >> 1;
+                    if (r <= xsh[mid])
+                        hi_ = mid;
+                    else
+                        lo_ = mid;
+                }
+            }
+            iv = hi_ - 1;
+            tt = r - xsh[iv];
+        }
+        const double* cf = coef + ((size_t)k * N + iv) * g.nlm * 4;
+        const double ct = dz * rinv;  // cos(theta); the reference takes cos(acos(z/r))
+        const double st = sqrt(1.0 - ct * ct);
+        const double rxy = sqrt(dx * dx + dy * dy);
+        double c1 = 1.0, s1 = 0.0;
+        if (rxy > 0.0) {
+            c1 = dx / rxy;
+            s1 = dy / rxy;
+        }
+        double cm = 1.0, sn = 0.0;  // cos(m phi), sin(m phi)
+        double pmm = 1.0;           // P_m^m
+        double fact = 1.0;
+        double sum = 0.0;
+        for (int m = 0; m <= L; m++) {
+            if (m > 0) {
+                pmm *= -fact * st;
+                fact += 2.0;
+                const double cn = cm * c1 - sn * s1;
+                sn = sn * c1 + cm * s1;
+                cm = cn;
+            }
+            double pl2 = 0.0, pl1 = pmm;  // P_{l-2}^m, P_{l-1}^m while iterating l
+            for (int l = m; l <= L; l++) {
+                double pl;
+                if (l == m)
+                    pl = pmm;
+                else if (l == m + 1)
+                    pl = ct * (double)(2 * m + 1) * pmm;
+                else
+                    pl = ((double)(2 * l - 1) * ct * pl1 + (double)(-l - m + 1) * pl2) * rj[l - m];
+                pl2 = pl1;
+                pl1 = pl;
+                const double pf = presh[l * (L + 1) + m] * rinv;
+                const int lmp = l * l + l + m;
+                {
+                    const double4 c = *reinterpret_cast<const double4*>(cf + (size_t)lmp * 4);
+                    const double sv = c.x + c.y * tt + c.z * tt * tt + c.w * tt * tt * tt;
+                    sum += pf * (pl * cm) * sv;
+                }
+                if (m > 0) {
+                    const double4 c = *reinterpret_cast<const double4*>(cf + (size_t)(lmp - 2 * m) * 4);
+                    const double sv = c.x + c.y * tt + c.z * tt * tt + c.w * tt * tt * tt;
+                    sum += pf * (pl * sn) * sv;
+                }
+            }
+        }
+        Vacc += sum;
+    }
+    V[p] = Vacc;
+    dJ[p] = w[p] * Vacc;
+}
+
+}  // namespace dfg

@@ -1,0 +1,239 @@
+"""ctypes view of the C ABI (include/dftgrid.h, built as dftcxx_b200/libdftgrid.so) with the method names
+of the reference's MolecularGrid (reference src/moleculargrid.h:84-167).  Plumbing only: every number is
+produced by the CUDA library; there is no Python or CPU compute path and a missing library is a hard error.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .molecule import LEBEDEV_COUNTS
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdftgrid.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+T_NAMES = ["points", "becke", "phi", "rho", "xc_point", "rho_lm", "poisson", "interp", "contract", "comm", "total"]
+
+
+class _System(C.Structure):
+    _fields_ = [("natoms", C.c_int), ("Z", _ip), ("xyz", _dp), ("nbf", C.c_int), ("bf_nprim", _ip), ("bf_center", _dp),
+                ("nprim", C.c_int), ("alpha", _dp), ("coeff", _dp), ("norm", _dp), ("lmn", _ip)]
+
+
+class _Params(C.Structure):
+    _fields_ = [("radial_points", C.c_int), ("lebedev_order", C.c_int), ("lmax", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libdftgrid.so (fails loudly if the CUDA extension has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("dftcxx_b200/libdftgrid.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.dftgrid_last_error.restype = C.c_char_p
+    L.dftgrid_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_System), C.POINTER(_Params), C.c_int, C.c_int, C.c_int]
+    L.dftgrid_destroy.argtypes = [C.c_void_p]
+    L.dftgrid_destroy.restype = None
+    L.dftgrid_comm_unique_id.argtypes = [C.c_void_p]
+    L.dftgrid_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    for n in ("dftgrid_build", "dftgrid_iteration_device", "dftgrid_synchronize"):
+        getattr(L, n).argtypes = [C.c_void_p]
+    for n in ("dftgrid_npoints", "dftgrid_npoints_local", "dftgrid_point_offset", "dftgrid_launch_count"):
+        getattr(L, n).argtypes = [C.c_void_p]
+        getattr(L, n).restype = C.c_long
+    for n in ("dftgrid_nbf", "dftgrid_nlm"):
+        getattr(L, n).argtypes = [C.c_void_p]
+    for n in ("dftgrid_set_density", "dftgrid_hartree_J", "dftgrid_electron_count", "dftgrid_upload_density",
+              "dftgrid_get_positions", "dftgrid_get_weights", "dftgrid_get_becke_weights", "dftgrid_get_densities",
+              "dftgrid_get_amplitudes", "dftgrid_get_potential", "dftgrid_get_rho_lm", "dftgrid_get_U_lm"):
+        getattr(L, n).argtypes = [C.c_void_p, _dp]
+    L.dftgrid_xc.argtypes = [C.c_void_p, _dp, _dp]
+    L.dftgrid_iteration.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp]
+    L.dftgrid_download_results.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    L.dftgrid_last_timings.argtypes = [C.c_void_p, _dp, C.c_int]
+    _lib = L
+    return L
+
+
+def _ptr(a, typ=_dp):
+    return a.ctypes.data_as(typ)
+
+
+class GridError(RuntimeError):
+    pass
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    if lib().dftgrid_comm_unique_id(buf) != 0:
+        raise GridError(lib().dftgrid_last_error().decode())
+    return buf.raw
+
+
+class MolecularGrid:
+    """B200 grid engine handle.  mol: anything with Z, xyz, bf_nprim, bf_center, alpha, coeff, norm, lmn arrays
+    (dftcxx_b200.molecule.Molecule or the dict oracle/refpy.Ref.system() returns)."""
+
+    def __init__(self, mol, device=0, rank=0, nranks=1):
+        get = (lambda k: mol[k]) if isinstance(mol, dict) else (lambda k: getattr(mol, k))
+        self._keep = dict(
+            Z=np.ascontiguousarray(get("Z"), dtype=np.int32), xyz=np.ascontiguousarray(get("xyz"), dtype=np.float64),
+            bf_nprim=np.ascontiguousarray(get("bf_nprim"), dtype=np.int32),
+            bf_center=np.ascontiguousarray(get("bf_center"), dtype=np.float64),
+            alpha=np.ascontiguousarray(get("alpha"), dtype=np.float64), coeff=np.ascontiguousarray(get("coeff"), dtype=np.float64),
+            norm=np.ascontiguousarray(get("norm"), dtype=np.float64), lmn=np.ascontiguousarray(get("lmn"), dtype=np.int32))
+        self.natoms = len(self._keep["Z"])
+        self.nbf = len(self._keep["bf_nprim"])
+        self.nprim = len(self._keep["alpha"])
+        self.device, self.rank, self.nranks = device, rank, nranks
+        self.h = None
+        self.radial_points = self.lebedev_order = self.lmax = None
+
+    # -- reference surface --------------------------------------------------------------------------------
+    def set_grid_parameters(self, radial_points, lebedev_order, lmax):
+        """MolecularGrid::set_grid_parameters (src/moleculargrid.cpp:175-179)."""
+        self.radial_points, self.lebedev_order, self.lmax = int(radial_points), int(lebedev_order), int(lmax)
+
+    def create_grid(self, comm_id=None):
+        """MolecularGrid::create_grid (src/moleculargrid.cpp:193-261)."""
+        if self.radial_points is None:
+            raise GridError("set_grid_parameters has not been called")
+        k = self._keep
+        sysd = _System(self.natoms, _ptr(k["Z"], _ip), _ptr(k["xyz"]), self.nbf, _ptr(k["bf_nprim"], _ip), _ptr(k["bf_center"]),
+                       self.nprim, _ptr(k["alpha"]), _ptr(k["coeff"]), _ptr(k["norm"]), _ptr(k["lmn"], _ip))
+        prm = _Params(self.radial_points, self.lebedev_order, self.lmax)
+        h = C.c_void_p()
+        self._ck(lib().dftgrid_create(C.byref(h), C.byref(sysd), C.byref(prm), self.device, self.rank, self.nranks))
+        self.h = h
+        if self.nranks > 1:
+            if comm_id is None:
+                raise GridError("nranks > 1 needs the NCCL unique id from rank 0")
+            self._ck(lib().dftgrid_comm_init(self.h, comm_id))
+        self._ck(lib().dftgrid_build(self.h))
+        self.npoints = lib().dftgrid_npoints(self.h)
+        self.nloc = lib().dftgrid_npoints_local(self.h)
+        self.point_offset = lib().dftgrid_point_offset(self.h)
+        self.nlm = lib().dftgrid_nlm(self.h)
+        self.nang = LEBEDEV_COUNTS[self.lebedev_order]
+
+    def set_density(self, P):
+        """set_density + correct_densities (src/moleculargrid.cpp:48-53,132-146)."""
+        self._ck(lib().dftgrid_set_density(self.h, _ptr(self._mat(P))))
+
+    def correct_densities(self):
+        """Folded into set_density (the reference always calls them back to back, src/dft.cpp:362-365)."""
+
+    def calculate_hartree_potential(self):
+        """MolecularGrid::calculate_hartree_potential (src/moleculargrid.cpp:336-389) -> J."""
+        J = np.zeros((self.nbf, self.nbf))
+        self._ck(lib().dftgrid_hartree_J(self.h, _ptr(J)))
+        return J
+
+    def calculate_exchange_correlation(self):
+        """DFT::calculate_exchange_correlation_matrix (src/dft.cpp:394-433) -> (XC, E_xc)."""
+        XC = np.zeros((self.nbf, self.nbf))
+        exc = C.c_double()
+        self._ck(lib().dftgrid_xc(self.h, _ptr(XC), C.cast(C.byref(exc), _dp)))
+        return XC, exc.value
+
+    def calculate_density(self):
+        """MolecularGrid::calculate_density (src/moleculargrid.cpp:157-166)."""
+        n = C.c_double()
+        self._ck(lib().dftgrid_electron_count(self.h, C.cast(C.byref(n), _dp)))
+        return n.value
+
+    def iteration(self, P):
+        """One SCF iteration's grid work through the single-call entry point -> (J, XC, E_xc, N_el)."""
+        J = np.zeros((self.nbf, self.nbf))
+        XC = np.zeros((self.nbf, self.nbf))
+        exc, nel = C.c_double(), C.c_double()
+        self._ck(lib().dftgrid_iteration(self.h, _ptr(self._mat(P)), _ptr(J), _ptr(XC), C.cast(C.byref(exc), _dp),
+                                         C.cast(C.byref(nel), _dp)))
+        return J, XC, exc.value, nel.value
+
+    # -- device-resident path (benchmarks) ---------------------------------------------------------------
+    def upload_density(self, P):
+        self._ck(lib().dftgrid_upload_density(self.h, _ptr(self._mat(P))))
+
+    def iteration_device(self):
+        self._ck(lib().dftgrid_iteration_device(self.h))
+
+    def synchronize(self):
+        self._ck(lib().dftgrid_synchronize(self.h))
+
+    def download_results(self):
+        J = np.zeros((self.nbf, self.nbf))
+        XC = np.zeros((self.nbf, self.nbf))
+        exc, nel = C.c_double(), C.c_double()
+        self._ck(lib().dftgrid_download_results(self.h, _ptr(J), _ptr(XC), C.cast(C.byref(exc), _dp), C.cast(C.byref(nel), _dp)))
+        return J, XC, exc.value, nel.value
+
+    # -- getters -------------------------------------------------------------------------------------------
+    def _vec(self, fn, shape):
+        out = np.zeros(shape)
+        self._ck(fn(self.h, _ptr(out)))
+        return out
+
+    def get_positions(self):
+        return self._vec(lib().dftgrid_get_positions, (self.nloc, 3))
+
+    def get_weights(self):
+        return self._vec(lib().dftgrid_get_weights, self.nloc)
+
+    def get_becke_weights(self):
+        return self._vec(lib().dftgrid_get_becke_weights, self.nloc)
+
+    def get_densities(self):
+        return self._vec(lib().dftgrid_get_densities, self.nloc)
+
+    def get_amplitudes(self):
+        """[nloc][nbf] (the reference returns the transpose, basis functions x points, src/moleculargrid.cpp:109-127)."""
+        return self._vec(lib().dftgrid_get_amplitudes, (self.nloc, self.nbf))
+
+    def get_potential(self):
+        return self._vec(lib().dftgrid_get_potential, self.nloc)
+
+    def get_rho_lm(self):
+        return self._vec(lib().dftgrid_get_rho_lm, (self.natoms, self.radial_points, self.nlm))
+
+    def get_U_lm(self):
+        return self._vec(lib().dftgrid_get_U_lm, (self.natoms, self.radial_points, self.nlm))
+
+    def timings(self):
+        t = np.zeros(len(T_NAMES))
+        self._ck(lib().dftgrid_last_timings(self.h, _ptr(t), len(T_NAMES)))
+        return dict(zip(T_NAMES, t.tolist()))
+
+    def launch_count(self):
+        return lib().dftgrid_launch_count(self.h)
+
+    # -- plumbing ------------------------------------------------------------------------------------------
+    def _mat(self, M):
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        if M.shape != (self.nbf, self.nbf):
+            raise GridError("matrix must be nbf x nbf")
+        return M
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GridError(lib().dftgrid_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().dftgrid_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

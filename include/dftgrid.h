@@ -1,0 +1,141 @@
+/*
+ * dftgrid.h — C ABI of the B200-native numerical-grid engine for dftcxx.
+ *
+ * This is the drop-in boundary for the per-SCF-iteration grid hot path.  The
+ * reference (ifilot/dftcxx) has no FFI; the boundary is the public surface of
+ * its MolecularGrid class as used by DFT (reference src/moleculargrid.h:84-167,
+ * call sites src/dft.cpp:57-61, 362-365, 483, 395-432, 111).  Every entry point
+ * below names the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain C types only; all buffers are caller-owned HOST memory, FP64.
+ *  - matrices are nb x nb, symmetric, column-major (Eigen's MatrixXd layout).
+ *  - point order is the reference's: atom-major, then radial index p-1 (r descending),
+ *    then Lebedev index (src/atomicgrid.cpp:50-82).  Basis-function order is whatever
+ *    the caller passes (the reference's is by element, src/molecule.cpp:222-235).
+ *  - every call returns 0 on success, non-zero on failure; dftgrid_last_error() then
+ *    holds a message (the reference throws std::runtime_error; the C++ host wrapper
+ *    in dftcxx_b200/host rethrows).  No C++ exception crosses this boundary.
+ *  - a handle is not re-entrant; calls come from one host thread (src/dft.cpp:95-104).
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Multi-GPU: one handle per process/GPU ("rank").  Grid points are sharded by
+ * (atom, radial shell) units; dftgrid_comm_* wires an NCCL communicator between
+ * the handles of one job (ids are exchanged by the host, e.g. torch.distributed).
+ */
+#ifndef DFTGRID_H
+#define DFTGRID_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dftgrid dftgrid_t;
+
+/* Molecule + basis, flattened.  Replaces the Molecule/Atom/CGF/GTO accessors the reference grid code
+ * reads (src/molecule.h:111-175, src/cgf.h:41-314). */
+typedef struct dftgrid_system {
+    int natoms;
+    const int* Z;             /* [natoms] nuclear charges                                   */
+    const double* xyz;        /* [natoms][3] positions in bohr                               */
+    int nbf;                  /* number of contracted basis functions (CGFs)                 */
+    const int* bf_nprim;      /* [nbf] primitives per CGF                                    */
+    const double* bf_center;  /* [nbf][3] centre of each CGF (bohr)                          */
+    int nprim;                /* total primitives = sum(bf_nprim)                            */
+    const double* alpha;      /* [nprim] exponents, CGF after CGF                            */
+    const double* coeff;      /* [nprim] contraction coefficients                            */
+    const double* norm;       /* [nprim] GTO normalisation constants (src/cgf.cpp:102-114)    */
+    const int* lmn;           /* [nprim][3] Cartesian powers, l+m+n <= 2 (src/cgf.cpp:185-232) */
+} dftgrid_system;
+
+/* MolecularGrid::set_grid_parameters (src/moleculargrid.cpp:175-179; presets src/settings.cpp:158-187) */
+typedef struct dftgrid_params {
+    int radial_points;  /* Gauss-Chebyshev nodes per atom                                    */
+    int lebedev_order;  /* index 0..10 into {6,14,26,38,50,74,86,110,146,170,194}            */
+    int lmax;           /* highest l of the multipole expansion of the Hartree potential     */
+} dftgrid_params;
+
+const char* dftgrid_last_error(void);
+/* ABI version of this header; bump on any signature change. */
+int dftgrid_abi_version(void);
+
+/* MolecularGrid::MolecularGrid + set_grid_parameters (src/moleculargrid.cpp:32-35,175-179).
+ * device: CUDA ordinal.  rank/nranks: this handle's shard of the grid (0/1 = whole grid). */
+int dftgrid_create(dftgrid_t** h, const dftgrid_system* sys, const dftgrid_params* prm, int device, int rank, int nranks);
+/* RAII teardown of unique_ptr<MolecularGrid> (src/dft.h:44). */
+void dftgrid_destroy(dftgrid_t* h);
+
+/* NCCL wiring for nranks > 1.  id is a 128-byte opaque blob produced on rank 0 and handed to every rank. */
+int dftgrid_comm_unique_id(void* id128);
+int dftgrid_comm_init(dftgrid_t* h, const void* id128);
+
+/* MolecularGrid::create_grid (src/moleculargrid.cpp:193-261): points, quadrature weights, CGF amplitudes,
+ * Becke weights; also factorises the radial Poisson operators used by dftgrid_hartree_J. */
+int dftgrid_build(dftgrid_t* h);
+
+/* sizes */
+long dftgrid_npoints(const dftgrid_t* h);        /* whole molecule                                     */
+long dftgrid_npoints_local(const dftgrid_t* h);  /* this rank's shard                                  */
+long dftgrid_point_offset(const dftgrid_t* h);   /* global index of the first local point              */
+int dftgrid_nbf(const dftgrid_t* h);
+int dftgrid_nlm(const dftgrid_t* h);
+
+/* MolecularGrid::set_density + correct_densities (src/moleculargrid.cpp:48-53,132-146; src/dft.cpp:362-365):
+ * rho_p = 2 phi_p^T P phi_p, then rho *= sum(Z)/sum(w rho). */
+int dftgrid_set_density(dftgrid_t* h, const double* P);
+/* MolecularGrid::calculate_hartree_potential (src/moleculargrid.cpp:336-389): J from the current density. */
+int dftgrid_hartree_J(dftgrid_t* h, double* J);
+/* DFT::calculate_exchange_correlation_matrix (src/dft.cpp:394-433) incl. Functional::xalpha_x_functional /
+ * vwm_c_functional (src/functionals.cpp:24-114): XC matrix and E_xc. */
+int dftgrid_xc(dftgrid_t* h, double* XC, double* exc);
+/* MolecularGrid::calculate_density (src/moleculargrid.cpp:157-166): sum(w rho). */
+int dftgrid_electron_count(dftgrid_t* h, double* nelec);
+
+/* One SCF iteration's whole grid path in one call (set_density, hartree_J, xc, electron_count with a single
+ * upload of P and a single download of [J | XC | exc | nelec]); same results as the four calls above. */
+int dftgrid_iteration(dftgrid_t* h, const double* P, double* J, double* XC, double* exc, double* nelec);
+
+/* Device-resident variant for benchmarking: P already uploaded by dftgrid_upload_density; runs all kernels and the
+ * collectives, leaves results on the device; dftgrid_download_results copies them out. */
+int dftgrid_upload_density(dftgrid_t* h, const double* P);
+int dftgrid_iteration_device(dftgrid_t* h);
+int dftgrid_download_results(dftgrid_t* h, double* J, double* XC, double* exc, double* nelec);
+int dftgrid_synchronize(dftgrid_t* h);
+
+/* Getters mirroring MolecularGrid::get_weights / get_densities / get_amplitudes (src/moleculargrid.cpp:61-127)
+ * plus parity/debug views of the intermediates.  All return this rank's LOCAL points, in order, except the
+ * per-atom tables which are whole-molecule. */
+int dftgrid_get_positions(dftgrid_t* h, double* xyz /* [nloc][3] */);
+int dftgrid_get_weights(dftgrid_t* h, double* w /* [nloc] */);
+int dftgrid_get_becke_weights(dftgrid_t* h, double* wb /* [nloc] */);
+int dftgrid_get_densities(dftgrid_t* h, double* rho /* [nloc] */);
+int dftgrid_get_amplitudes(dftgrid_t* h, double* phi /* [nloc][nbf], point-major */);
+int dftgrid_get_potential(dftgrid_t* h, double* V /* [nloc] Hartree potential */);
+int dftgrid_get_rho_lm(dftgrid_t* h, double* rho_lm /* [natoms][nrad][nlm] */);
+int dftgrid_get_U_lm(dftgrid_t* h, double* U_lm /* [natoms][nrad][nlm] */);
+
+/* Per-phase device times (CUDA events on the handle's stream) of the most recent build / iteration, in ms.
+ * Slots: see DFTGRID_T_* below.  n = number of doubles available in out. */
+int dftgrid_last_timings(dftgrid_t* h, double* out, int n);
+/* Kernel launches issued by this handle since creation. */
+long dftgrid_launch_count(const dftgrid_t* h);
+
+enum {
+    DFTGRID_T_POINTS = 0,   /* build: points + raw weights            */
+    DFTGRID_T_BECKE = 1,    /* build: Becke fuzzy-cell weights        */
+    DFTGRID_T_PHI = 2,      /* build: CGF amplitudes                  */
+    DFTGRID_T_RHO = 3,      /* iteration: rho = 2 rowsum((Phi P) o Phi) */
+    DFTGRID_T_XCPOINT = 4,  /* iteration: charge sums, rescale, LDA pointwise */
+    DFTGRID_T_RHOLM = 5,    /* iteration: Ylm projection              */
+    DFTGRID_T_POISSON = 6,  /* iteration: radial solves, own-cell V, splines */
+    DFTGRID_T_INTERP = 7,   /* iteration: cross-atom interpolation    */
+    DFTGRID_T_CONTRACT = 8, /* iteration: [J | XC] contraction + reduction */
+    DFTGRID_T_COMM = 9,     /* iteration: collectives                 */
+    DFTGRID_T_TOTAL = 10,   /* iteration: first kernel to last        */
+    DFTGRID_T_COUNT = 11
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFTGRID_H */
