@@ -113,12 +113,17 @@ class MolecularGrid:
         prm = _Params(self.radial_points, self.lebedev_order, self.lmax)
         h = C.c_void_p()
         self._ck(lib().dftgrid_create(C.byref(h), C.byref(sysd), C.byref(prm), self.device, self.rank, self.nranks))
+        self.close()
         self.h = h
-        if self.nranks > 1:
-            if comm_id is None:
-                raise GridError("nranks > 1 needs the NCCL unique id from rank 0")
-            self._ck(lib().dftgrid_comm_init(self.h, comm_id))
-        self._ck(lib().dftgrid_build(self.h))
+        try:
+            if self.nranks > 1:
+                if comm_id is None:
+                    raise GridError("nranks > 1 needs the NCCL unique id from rank 0")
+                self._ck(lib().dftgrid_comm_init(self.h, comm_id))
+            self._ck(lib().dftgrid_build(self.h))
+        except GridError:
+            self.close()
+            raise
         self.npoints = lib().dftgrid_npoints(self.h)
         self.nloc = lib().dftgrid_npoints_local(self.h)
         self.point_offset = lib().dftgrid_point_offset(self.h)

