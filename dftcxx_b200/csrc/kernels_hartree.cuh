@@ -296,7 +296,7 @@ k_interp(GridShape g, const double* __restrict__ atom_xyz, const double* __restr
             tt = r - xsh[iv];
         }
         const double* cf = coef + ((size_t)k * N + iv) * g.nlm * 4;
-        const double ct = dz * rinv;  // cos(theta); the reference takes cos(acos(z/r))
+        const double ct = dz / r;  // cos(theta) = z/r by true division (exactly +-1 on the axis, like the reference's cos(acos(z/r)))
         const double st = sqrt(1.0 - ct * ct);
         const double rxy = sqrt(dx * dx + dy * dy);
         double c1 = 1.0, s1 = 0.0;
