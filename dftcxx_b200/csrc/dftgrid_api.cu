@@ -107,12 +107,15 @@ struct dftgrid {
 
     // timing
     cudaEvent_t ev[16]{};
+    cudaEvent_t ev_sw[2]{};
     bool ev_build = false, ev_iter = false;
     double t_ms[DFTGRID_T_COUNT]{};
 
     ~dftgrid() {
         if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
         for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        for (auto& e : ev_sw)
             if (e) cudaEventDestroy(e);
         if (h_P) cudaFreeHost(h_P);
         if (h_res) cudaFreeHost(h_res);
@@ -534,6 +537,7 @@ int dftgrid_create(dftgrid_t** out, const dftgrid_system* sys, const dftgrid_par
         if (prop.major < 10) throw std::runtime_error("this library is built for sm_100a (B200) only");
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+        for (auto& ev : h->ev_sw) CK(cudaEventCreate(&ev));
         *out = h.release();
     });
 }
@@ -723,6 +727,24 @@ int dftgrid_last_timings(dftgrid_t* h, double* out, int n) {
         CK(cudaStreamSynchronize(h->stream));
         if (h->timed_iter) finish_timings(h);
         for (int i = 0; i < n && i < DFTGRID_T_COUNT; i++) out[i] = h->t_ms[i];
+    });
+}
+
+int dftgrid_timer_start(dftgrid_t* h) {
+    return guarded([&] {
+        use_device(h);
+        CK(cudaEventRecord(h->ev_sw[0], h->stream));
+    });
+}
+
+int dftgrid_timer_stop(dftgrid_t* h, double* ms) {
+    return guarded([&] {
+        use_device(h);
+        CK(cudaEventRecord(h->ev_sw[1], h->stream));
+        CK(cudaEventSynchronize(h->ev_sw[1]));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, h->ev_sw[0], h->ev_sw[1]));
+        *ms = t;
     });
 }
 

@@ -45,7 +45,8 @@ def lib():
     L.dftgrid_destroy.restype = None
     L.dftgrid_comm_unique_id.argtypes = [C.c_void_p]
     L.dftgrid_comm_init.argtypes = [C.c_void_p, C.c_void_p]
-    for n in ("dftgrid_build", "dftgrid_iteration_device", "dftgrid_synchronize"):
+    L.dftgrid_timer_stop.argtypes = [C.c_void_p, _dp]
+    for n in ("dftgrid_build", "dftgrid_iteration_device", "dftgrid_synchronize", "dftgrid_timer_start"):
         getattr(L, n).argtypes = [C.c_void_p]
     for n in ("dftgrid_npoints", "dftgrid_npoints_local", "dftgrid_point_offset", "dftgrid_launch_count"):
         getattr(L, n).argtypes = [C.c_void_p]
@@ -174,6 +175,14 @@ class MolecularGrid:
 
     def synchronize(self):
         self._ck(lib().dftgrid_synchronize(self.h))
+
+    def timer_start(self):
+        self._ck(lib().dftgrid_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(lib().dftgrid_timer_stop(self.h, C.cast(C.byref(ms), _dp)))
+        return ms.value
 
     def download_results(self):
         J = np.zeros((self.nbf, self.nbf))

@@ -117,6 +117,10 @@ int dftgrid_get_U_lm(dftgrid_t* h, double* U_lm /* [natoms][nrad][nlm] */);
 /* Per-phase device times (CUDA events on the handle's stream) of the most recent build / iteration, in ms.
  * Slots: see DFTGRID_T_* below.  n = number of doubles available in out. */
 int dftgrid_last_timings(dftgrid_t* h, double* out, int n);
+/* Device stopwatch on the handle's stream (CUDA events): start records an event now, stop records a second one, waits
+ * for it and returns the elapsed device time in ms.  Used by bench.py to time K iterations where the work is queued. */
+int dftgrid_timer_start(dftgrid_t* h);
+int dftgrid_timer_stop(dftgrid_t* h, double* ms);
 /* Kernel launches issued by this handle since creation. */
 long dftgrid_launch_count(const dftgrid_t* h);
 

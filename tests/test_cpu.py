@@ -153,9 +153,10 @@ def test_reference_oracle_reproduces_golden_and_survey_anchors():
     xyz, w, wb = r.grid()
     assert np.array_equal(xyz[g["idx"]], g["pts"]) and np.array_equal(wb[g["idx"]], g["wb"])
     r.set_density(g["P"])
-    assert np.array_equal(r.hartree(), g["J"])
+    # the reference's own OpenMP reductions (src/atomicgrid.cpp:523) reorder sums from run to run: not bitwise
+    assert np.max(np.abs(r.hartree() - g["J"])) < 1e-12
     XC, exc = r.xc()
-    assert np.max(np.abs(XC - g["XC"])) < 1e-13  # the reference's own OpenMP reductions reorder sums run to run
+    assert np.max(np.abs(XC - g["XC"])) < 1e-12
     r.close()
     e = g["scf_energies"][:, 0]
     assert len(e) == 14 and round(e[0], 7) == -72.1721582 and round(e[-1], 7) == -72.9906070
