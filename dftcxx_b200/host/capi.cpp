@@ -1,0 +1,88 @@
+// C entry points of the host program for tests (ctypes): run the SCF, or just the host-only pieces (integrals,
+// eigen-solver) that can be checked on a machine without a GPU.
+#include <cstring>
+#include <string>
+
+#include "dft.hpp"
+
+namespace {
+thread_local std::string g_err;
+}
+
+extern "C" {
+
+const char* dfthost_last_error() { return g_err.c_str(); }
+
+// energies: [max_iter][6] = et, exc, e_one, e_j, nelec_grid, ms ; returns the number of iterations run, < 0 on error.
+// fixed_iterations > 0 runs exactly that many loop bodies (comparison at equal iteration index), otherwise the
+// reference's stopping rule (|dE| <= 1e-4 and >= 3 iterations) applies.
+int dfthost_scf(const char* infile, int device, int fixed_iterations, int max_iter, double* energies, double* enuc) {
+    try {
+        dftcxx::DFT dft(infile, device, false);
+        if (fixed_iterations > 0)
+            for (int i = 0; i < fixed_iterations && i < max_iter; i++) dft.scf_step();
+        else
+            dft.scf((unsigned)max_iter);
+        const auto& h = dft.history();
+        int n = 0;
+        for (const auto& r : h) {
+            if (n >= max_iter) break;
+            double* e = energies + 6 * n++;
+            e[0] = r.et;
+            e[1] = r.exc;
+            e[2] = r.e_one;
+            e[3] = r.e_j;
+            e[4] = r.nelec_grid;
+            e[5] = r.ms;
+        }
+        if (enuc) *enuc = dft.nuclear_repulsion();
+        return n;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// host-only: S, T, V (nb x nb each) for an input file; no GPU needed.  Returns nb or < 0.
+int dfthost_one_electron(const char* infile, int nb_cap, double* S, double* T, double* V) {
+    try {
+        auto st = std::make_shared<dftcxx::Settings>(infile);
+        auto mol = std::make_shared<dftcxx::Molecule>(infile, st, false);
+        const int n = (int)mol->get_nr_bfs();
+        if (n > nb_cap) return n;
+        dftcxx::Integrator integ;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                S[i * n + j] = integ.overlap(mol->get_cgf(i), mol->get_cgf(j));
+                T[i * n + j] = integ.kinetic(mol->get_cgf(i), mol->get_cgf(j));
+                double v = 0.0;
+                for (unsigned k = 0; k < mol->get_nr_atoms(); k++)
+                    v += integ.nuclear(mol->get_cgf(i), mol->get_cgf(j), mol->get_atomic_position(k), mol->get_atomic_charge(k));
+                V[i * n + j] = v;
+            }
+        return n;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// host-only: symmetric eigen-solver; A row-major n x n, w ascending, eigenvectors in the columns of Vout (row-major)
+int dfthost_sym_eigen(int n, const double* A, double* w, double* Vout) {
+    try {
+        dftcxx::Mat M(n, n);
+        std::memcpy(M.data(), A, sizeof(double) * n * n);
+        std::vector<double> ev;
+        dftcxx::Mat V;
+        dftcxx::sym_eigen(M, ev, V);
+        std::memcpy(w, ev.data(), sizeof(double) * n);
+        std::memcpy(Vout, V.data(), sizeof(double) * n * n);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+void dfthost_boys(int nmax, double x, double* F) { dftcxx::Integrator::boys(nmax, x, F); }
+}

@@ -1,0 +1,174 @@
+#include "dft.hpp"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <stdexcept>
+
+namespace dftcxx {
+
+using clk = std::chrono::system_clock;
+static long ms_since(const clk::time_point& t0) { return (long)std::chrono::duration_cast<std::chrono::milliseconds>(clk::now() - t0).count(); }
+
+DFT::DFT(const std::string& filename, int device_, bool verbose_) : verbose(verbose_), device(device_) {
+    settings = std::make_shared<Settings>(filename);
+    mol = std::make_shared<Molecule>(filename, settings, verbose);
+    add_molecule();
+}
+
+void DFT::add_molecule() {
+    nelec = mol->get_nr_elec();
+    if (settings->get_hartree_evaluation_method() == Settings::TWO_ELECTRON_INTEGRALS)
+        throw std::runtime_error("hartree_evaluation = two_electron_integrals is outside this build's scope "
+                                 "(the GPU engine implements the becke_grid path); remove the key or set becke_grid");
+    molgrid.reset(new MolecularGrid(mol, device, verbose));
+    molgrid->set_grid_parameters(settings->get_radial_points(), settings->get_lebedev_order(), settings->get_lmax());
+    molgrid->create_grid();
+    cgfs = mol->get_cgfs();
+    if (verbose) std::cout << "Loading molecule and constructing matrices." << std::endl;
+    const auto t0 = clk::now();
+    construct_matrices();
+    if (verbose) {
+        std::printf("Total time: %ld ms\n", ms_since(t0));
+        std::cout << std::endl;
+    }
+}
+
+void DFT::construct_matrices() {
+    const unsigned int n = mol->get_nr_bfs();
+    S = Mat(n, n);
+    T = Mat(n, n);
+    V = Mat(n, n);
+    J = Mat(n, n);
+    XC = Mat(n, n);
+    P = Mat(n, n);
+#pragma omp parallel for schedule(dynamic)
+    for (unsigned int i = 0; i < n; i++)
+        for (unsigned int j = i; j < n; j++) {
+            S(i, j) = S(j, i) = integrator.overlap((*cgfs)[i], (*cgfs)[j]);
+            T(i, j) = T(j, i) = integrator.kinetic((*cgfs)[i], (*cgfs)[j]);
+            double v = 0.0;
+            for (unsigned int k = 0; k < mol->get_nr_atoms(); k++)
+                v += integrator.nuclear((*cgfs)[i], (*cgfs)[j], mol->get_atomic_position(k), mol->get_atomic_charge(k));
+            V(i, j) = V(j, i) = v;
+        }
+    H = Mat(n, n);
+    for (unsigned int i = 0; i < n; i++)
+        for (unsigned int j = 0; j < n; j++) H(i, j) = T(i, j) + V(i, j);
+    calculate_nuclear_repulsion();
+    calculate_transformation_matrix();
+    calculate_density_matrix();              // core-Hamiltonian guess: J = XC = 0 here
+    calculate_electronic_repulsion_matrix();
+    calculate_energy();                      // exc is still zero at this point (the reference reads it uninitialised)
+}
+
+void DFT::calculate_nuclear_repulsion() {
+    enuc = 0.0;
+    for (unsigned int i = 0; i < mol->get_nr_atoms(); i++)
+        for (unsigned int j = i + 1; j < mol->get_nr_atoms(); j++) {
+            const vec3 &a = mol->get_atomic_position(i), &b = mol->get_atomic_position(j);
+            const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+            enuc += (double)mol->get_atomic_charge(i) * (double)mol->get_atomic_charge(j) / std::sqrt(dx * dx + dy * dy + dz * dz);
+        }
+}
+
+// canonical orthogonalisation X = U s^{-1/2} (src/dft.cpp:300-316)
+void DFT::calculate_transformation_matrix() {
+    const unsigned int n = mol->get_nr_bfs();
+    std::vector<double> w;
+    Mat U;
+    sym_eigen(S, w, U);
+    X = Mat(n, n);
+    for (unsigned int i = 0; i < n; i++)
+        for (unsigned int j = 0; j < n; j++) X(i, j) = U(i, j) * (1.0 / std::sqrt(w[j]));
+    Xp = transpose(X);
+}
+
+// F = H + 2J + XC -> F' = X^T F X -> C = X C' -> P from the nelec/2 lowest orbitals, 50 % linear mixing after the
+// first density; then the grid density is refreshed (src/dft.cpp:330-366)
+void DFT::calculate_density_matrix() {
+    const double alpha = 0.50;
+    const unsigned int n = mol->get_nr_bfs();
+    Mat F(n, n);
+    for (unsigned int i = 0; i < n; i++)
+        for (unsigned int j = 0; j < n; j++) F(i, j) = H(i, j) + 2.0 * J(i, j) + XC(i, j);
+    const Mat Fp = matmul(matmul(Xp, F), X);
+    std::vector<double> eps;
+    Mat Cc;
+    sym_eigen(Fp, eps, Cc);
+    C = matmul(X, Cc);
+    const unsigned int nocc = nelec / 2;
+    Mat Pnew(n, n, 0.0);
+    for (unsigned int i = 0; i < n; i++)
+        for (unsigned int j = 0; j < n; j++) {
+            double s = 0.0;
+            for (unsigned int k = 0; k < nocc; k++) s += C(i, k) * C(j, k);
+            Pnew(i, j) = s;
+        }
+    if (is_first) {
+        P = Pnew;
+        is_first = false;
+    } else {
+        for (unsigned int i = 0; i < n; i++)
+            for (unsigned int j = 0; j < n; j++) P(i, j) = (1.0 - alpha) * Pnew(i, j) + alpha * P(i, j);
+    }
+    molgrid->set_density(P);
+    molgrid->correct_densities();
+}
+
+void DFT::calculate_electronic_repulsion_matrix() { J = molgrid->calculate_hartree_potential(); }
+
+void DFT::calculate_exchange_correlation_matrix() { XC = molgrid->calculate_exchange_correlation(exc); }
+
+void DFT::calculate_energy() {
+    single_electron_energy = 2.0 * trace_of_product(P, H);
+    electronic_repulsion = 2.0 * trace_of_product(P, J);
+    et = single_electron_energy + electronic_repulsion + enuc + exc;
+}
+
+double DFT::scf_step() {
+    const auto t0 = clk::now();
+    calculate_density_matrix();
+    calculate_electronic_repulsion_matrix();
+    calculate_exchange_correlation_matrix();
+    calculate_energy();
+    records.push_back(ScfRecord{et, exc, single_electron_energy, electronic_repulsion, molgrid->calculate_density(), (double)ms_since(t0)});
+    return et;
+}
+
+void DFT::scf(unsigned int max_iterations, double threshold) {
+    if (verbose) {
+        std::cout << "          Starting calculation          " << std::endl;
+        std::cout << "========================================" << std::endl;
+        std::cout << "  #        energy    elec" << std::endl;
+        std::cout << "----------------------------------------" << std::endl;
+    }
+    double old_energy = et, difference = 1.0;
+    unsigned int iteration = 0;
+    while (difference > threshold || iteration < 3) {
+        iteration++;
+        scf_step();
+        const ScfRecord& r = records.back();
+        if (verbose) {
+            std::printf("%3u    %9.7f    %4.2f (%3u) \n", iteration, r.et, r.nelec_grid, nelec);
+            std::printf("\tE_XC \t= %9.7f\n\tE_NUC \t= %9.7f\n\tE_ONE \t= %9.7f\n\tE_J \t= %9.7f\n\tt \t=%9ld ms\n", r.exc, enuc, r.e_one, r.e_j, (long)r.ms);
+            std::cout << "----------------------------------------" << std::endl;
+        }
+        difference = std::fabs(et - old_energy);
+        old_energy = et;
+        if (iteration >= max_iterations) {
+            if (verbose) {
+                std::cout << "========================================" << std::endl;
+                std::cout << "Stopping because maximum number of iterations has been reached." << std::endl << std::endl;
+            }
+            break;
+        }
+    }
+    if (iteration < max_iterations && verbose) {
+        std::cout << "========================================" << std::endl;
+        std::cout << "Stopping because energy criterion is reached." << std::endl << std::endl;
+    }
+}
+
+}  // namespace dftcxx

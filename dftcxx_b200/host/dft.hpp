@@ -1,0 +1,64 @@
+// Closed-shell LDA Kohn-Sham SCF driver: the reference's DFT class (src/dft.h, src/dft.cpp) with the grid work
+// delegated to the GPU MolecularGrid.  One-electron integrals, the canonical orthogonalisation, the eigen-solve,
+// density mixing and the energy expression stay on the host exactly as in the reference.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "integrals.hpp"
+#include "linalg.hpp"
+#include "molecule.hpp"
+#include "moleculargrid.hpp"
+#include "settings.hpp"
+
+namespace dftcxx {
+
+struct ScfRecord {  // one line of the SCF table
+    double et, exc, e_one, e_j, nelec_grid, ms;
+};
+
+class DFT {
+public:
+    explicit DFT(const std::string& filename, int device = 0, bool verbose = true);
+    void scf(unsigned int max_iterations = 100, double threshold = 1e-4);
+
+    const std::vector<ScfRecord>& history() const { return records; }
+    const Mat& overlap_matrix() const { return S; }
+    const Mat& core_hamiltonian() const { return H; }
+    const Mat& kinetic_matrix() const { return T; }
+    const Mat& nuclear_matrix() const { return V; }
+    const Mat& density_matrix() const { return P; }
+    const Mat& coulomb_matrix() const { return J; }
+    const Mat& xc_matrix() const { return XC; }
+    double nuclear_repulsion() const { return enuc; }
+    double total_energy() const { return et; }
+    unsigned int nbf() const { return mol->get_nr_bfs(); }
+    // one pass of the loop body (src/dft.cpp:100-103); returns the total energy
+    double scf_step();
+
+private:
+    void add_molecule();
+    void construct_matrices();
+    void calculate_nuclear_repulsion();
+    void calculate_transformation_matrix();
+    void calculate_density_matrix();
+    void calculate_electronic_repulsion_matrix();
+    void calculate_exchange_correlation_matrix();
+    void calculate_energy();
+
+    std::shared_ptr<Settings> settings;
+    std::shared_ptr<Molecule> mol;
+    std::unique_ptr<MolecularGrid> molgrid;
+    Integrator integrator;
+    const std::vector<CGF>* cgfs = nullptr;
+    Mat S, T, V, H, X, Xp, C, P, J, XC;
+    unsigned int nelec = 0;
+    double exc = 0.0, enuc = 0.0, et = 0.0, single_electron_energy = 0.0, electronic_repulsion = 0.0;
+    bool is_first = true;
+    bool verbose;
+    int device;
+    std::vector<ScfRecord> records;
+};
+
+}  // namespace dftcxx

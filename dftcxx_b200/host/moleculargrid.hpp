@@ -1,0 +1,45 @@
+// MolecularGrid: the reference's grid class surface (src/moleculargrid.h:84-167) as a thin C++ view of the
+// B200 grid engine behind the C ABI (include/dftgrid.h).  All numerical work happens in libdftgrid.so's CUDA
+// kernels; a failing C-ABI call is rethrown as std::runtime_error, which is what the reference throws.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "../../include/dftgrid.h"
+#include "linalg.hpp"
+#include "molecule.hpp"
+
+namespace dftcxx {
+
+class MolecularGrid {
+public:
+    explicit MolecularGrid(const std::shared_ptr<Molecule>& mol, int device = 0, bool verbose = true);
+    ~MolecularGrid();
+    MolecularGrid(const MolecularGrid&) = delete;
+    MolecularGrid& operator=(const MolecularGrid&) = delete;
+
+    void set_grid_parameters(unsigned int radial_points, unsigned int lebedev_order, unsigned int lmax);
+    void create_grid();
+
+    void set_density(const Mat& P);  // rho = 2 phi^T P phi on every grid point
+    void correct_densities();        // rescale to the electron count (done on the device together with set_density)
+    double calculate_density() const;
+    Mat calculate_hartree_potential();                 // J
+    Mat calculate_exchange_correlation(double& exc);   // XC matrix + E_xc (DFT::calculate_exchange_correlation_matrix)
+
+    std::vector<double> get_weights() const;
+    std::vector<double> get_densities() const;
+    Mat get_amplitudes() const;  // basis functions x grid points, like the reference
+    size_t get_grid_size() const;
+
+private:
+    void check(int rc) const;
+    std::shared_ptr<Molecule> mol;
+    dftgrid_t* handle = nullptr;
+    unsigned int radial_points = 15, lebedev_order = 7, lmax = 8;
+    int device;
+    bool verbose;
+    bool density_pending = false;
+};
+
+}  // namespace dftcxx

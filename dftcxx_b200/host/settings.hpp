@@ -1,0 +1,44 @@
+// Input settings of a dftcxx run: the `key = value` lines that precede `system:` in a .in file, plus the grid
+// presets.  Same keys, defaults and precedence as the reference (src/settings.cpp:39-187): first occurrence of a
+// key wins, `grid` in {coarse, medium (default), fine, ultrafine}, optional overrides radial_points /
+// lebedev_order / lmax (ignored when not an unsigned integer), hartree_evaluation defaults to becke_grid.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace dftcxx {
+
+class Settings {
+public:
+    enum { BECKE_GRID, TWO_ELECTRON_INTEGRALS };
+    enum { GRID_COARSE, GRID_MEDIUM, GRID_FINE, GRID_ULTRAFINE };
+
+    explicit Settings(const std::string& filename);
+    static Settings from_text(const std::string& text);
+
+    const std::string& get_value(const std::string& key) const;  // throws std::logic_error when absent
+    bool has(const std::string& key) const { return key_values.count(key) != 0; }
+    unsigned int get_hartree_evaluation_method() const { return hartree_evaluation; }
+    unsigned int get_radial_points() const { return radial_points; }
+    unsigned int get_lebedev_order() const { return lebedev_order; }
+    unsigned int get_lmax() const { return lmax; }
+
+private:
+    Settings() {}
+    void parse(std::istream& in);
+    void set_default_settings();
+    void set_grid_fineness(unsigned int fineness);
+
+    std::unordered_map<std::string, std::string> key_values;
+    unsigned int radial_points = 15, lebedev_order = 7, lmax = 8;
+    unsigned int hartree_evaluation = BECKE_GRID;
+};
+
+// shared text helpers (boost::split(token_compress_on) / trim / strict lexical_cast semantics)
+std::vector<std::string> split_compress(const std::string& line, const std::string& seps);
+std::string trimmed(const std::string& s);
+bool parse_uint(const std::string& s, unsigned int& out);
+double parse_double(const std::string& s);  // throws std::runtime_error on junk
+
+}  // namespace dftcxx

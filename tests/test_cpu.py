@@ -167,3 +167,75 @@ def test_golden_scf_traces_match_survey_probe(name, iters, e_final):
     g = load_golden(name)
     assert len(g["scf_energies"]) == iters
     assert round(float(g["scf_energies"][-1, 0]), 7) == e_final
+
+
+# ---------------------------------------------------------------------------------------------- C++ host (CPU parts)
+def _hostlib():
+    path = os.path.join(ROOT, "dftcxx_b200", "libdfthost.so")
+    assert os.path.exists(path), "build the host first (__graft_entry__.build())"
+    L = ctypes.CDLL(path)
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.dfthost_one_electron.argtypes = [ctypes.c_char_p, ctypes.c_int, dp, dp, dp]
+    L.dfthost_sym_eigen.argtypes = [ctypes.c_int, dp, dp, dp]
+    L.dfthost_boys.argtypes = [ctypes.c_int, ctypes.c_double, dp]
+    L.dfthost_last_error.restype = ctypes.c_char_p
+    return L, dp
+
+
+@pytest.mark.parametrize("name", ["h2o_sto3g", "h2o_p631", "he_sto3g", "co_sto3g_coarse", "h2_sto3g_ultrafine", "ch4_p631_fine",
+                                  "ethane_p631_fine", "benzene_p631_fine"])
+def test_host_one_electron_integrals_match_reference(name):
+    """The host's McMurchie-Davidson S and H = T + V against the reference's own matrices (golden scf_S / scf_H):
+    an independent algorithm, so agreement also pins the truncated-pi prefactor and the Boys-argument clamp."""
+    L, dp = _hostlib()
+    g = load_golden(name)
+    nb = len(g["bf_nprim"])
+    S, T, V = (np.zeros((nb, nb)) for _ in range(3))
+    n = L.dfthost_one_electron(os.path.join(M.DATA, "molecules", name + ".in").encode(), nb, S.ctypes.data_as(dp),
+                               T.ctypes.data_as(dp), V.ctypes.data_as(dp))
+    assert n == nb, L.dfthost_last_error()
+    assert np.max(np.abs(S - g["scf_S"])) < 1e-14
+    assert np.max(np.abs(T + V - g["scf_H"])) < 1e-11
+    assert np.max(np.abs(S - S.T)) < 1e-15
+
+
+def test_host_eigensolver_against_numpy():
+    L, dp = _hostlib()
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 5, 30, 120):
+        A = rng.standard_normal((n, n))
+        A = A + A.T
+        if n == 30:
+            A[:6] = 0.0
+            A[:, :6] = 0.0  # six-fold degenerate eigenvalue 0
+        w, V = np.zeros(n), np.zeros((n, n))
+        assert L.dfthost_sym_eigen(n, np.ascontiguousarray(A).ctypes.data_as(dp), w.ctypes.data_as(dp), V.ctypes.data_as(dp)) == 0
+        assert np.max(np.abs(w - np.linalg.eigvalsh(A))) < 1e-12 * max(1.0, np.abs(A).max() * n)
+        assert np.all(np.diff(w) >= 0)
+        assert np.max(np.abs(A @ V - V * w)) < 1e-12 * n
+        assert np.max(np.abs(V.T @ V - np.eye(n))) < 1e-13 * n
+
+
+def test_host_boys_function():
+    from scipy.special import gammainc, gamma
+
+    L, dp = _hostlib()
+    F = np.zeros(5)
+    for x in (1e-8, 1e-3, 0.5, 7.0, 34.9, 35.1, 120.0):
+        L.dfthost_boys(4, x, F.ctypes.data_as(dp))
+        for n in range(5):
+            ref = 0.5 * x ** (-n - 0.5) * gamma(n + 0.5) * gammainc(n + 0.5, x)
+            assert abs(F[n] - ref) <= 2e-14 * ref, (x, n)
+
+
+def test_host_cli_argument_errors():
+    import subprocess
+
+    exe = os.path.join(ROOT, "dftcxx_b200", "bin", "dftcxx")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode != 0 and "Required argument missing" in r.stderr
+    r = subprocess.run([exe, "-i", "/nonexistent.in"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Cannot open /nonexistent.in!" in r.stderr
+    r = subprocess.run([exe, "--version"], capture_output=True, text=True)
+    assert r.returncode == 0 and "version" in r.stdout
