@@ -210,8 +210,7 @@ void do_build(dftgrid* h) {
     g.nlm = (prm.lmax + 1) * (prm.lmax + 1);
     g.npts = (long)g.natoms * g.nrad * g.nang;
     const long nshell = (long)g.natoms * g.nrad;
-    g.shell0 = nshell * h->rank / h->nranks;
-    g.nshell_loc = nshell * (h->rank + 1) / h->nranks - g.shell0;
+    dftgrid_shard_range(nshell, h->rank, h->nranks, &g.shell0, &g.nshell_loc);
     g.nloc = g.nshell_loc * g.nang;
     h->leb_off = lebedev_offset(prm.lebedev_order);
 
@@ -547,6 +546,16 @@ void dftgrid_destroy(dftgrid_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     delete h;
+}
+
+int dftgrid_shard_range(long nshell_total, int rank, int nranks, long* first_shell, long* nshell) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || nshell_total < 0 || !first_shell || !nshell) {
+        g_error = "dftgrid_shard_range: bad arguments";
+        return 1;
+    }
+    *first_shell = nshell_total * rank / nranks;
+    *nshell = nshell_total * (rank + 1) / nranks - *first_shell;
+    return 0;
 }
 
 int dftgrid_comm_unique_id(void* id128) {

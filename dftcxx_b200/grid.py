@@ -73,6 +73,16 @@ class GridError(RuntimeError):
     pass
 
 
+def shard_range(nshell_total, rank, nranks):
+    """(first_shell, nshell) of a rank — the C library's own rule (dftgrid_shard_range)."""
+    first, count = C.c_long(), C.c_long()
+    L = lib()
+    L.dftgrid_shard_range.argtypes = [C.c_long, C.c_int, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    if L.dftgrid_shard_range(nshell_total, rank, nranks, C.byref(first), C.byref(count)) != 0:
+        raise GridError(L.dftgrid_last_error().decode())
+    return first.value, count.value
+
+
 def comm_unique_id():
     buf = C.create_string_buffer(128)
     if lib().dftgrid_comm_unique_id(buf) != 0:

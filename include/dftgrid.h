@@ -65,6 +65,10 @@ int dftgrid_create(dftgrid_t** h, const dftgrid_system* sys, const dftgrid_param
 /* RAII teardown of unique_ptr<MolecularGrid> (src/dft.h:44). */
 void dftgrid_destroy(dftgrid_t* h);
 
+/* The shard of rank `rank` out of `nranks`: a contiguous block of the natoms*nrad (atom, radial shell) units, balanced by
+ * count.  Pure host arithmetic (no device needed); dftgrid_build uses exactly this rule. */
+int dftgrid_shard_range(long nshell_total, int rank, int nranks, long* first_shell, long* nshell);
+
 /* NCCL wiring for nranks > 1.  id is a 128-byte opaque blob produced on rank 0 and handed to every rank. */
 int dftgrid_comm_unique_id(void* id128);
 int dftgrid_comm_init(dftgrid_t* h, const void* id128);
