@@ -239,3 +239,33 @@ def test_host_cli_argument_errors():
     assert r.returncode != 0 and "Cannot open /nonexistent.in!" in r.stderr
     r = subprocess.run([exe, "--version"], capture_output=True, text=True)
     assert r.returncode == 0 and "version" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------- plain-C restatement
+@pytest.mark.parametrize("name", ["h2o_sto3g", "he_sto3g", "co_sto3g_coarse", "ch4_p631_fine"])
+def test_c_restatement_matches_reference_golden(name):
+    """oracle/oracle_port.c (the portable restatement) against the vectors the unmodified reference produced."""
+    from oracle import portpy
+
+    if not portpy.available():
+        pytest.skip("oracle/liboracle.so not built")
+    g = load_golden(name)
+    o = portpy.Port({k: g[k] for k in ("Z", "xyz", "bf_nprim", "bf_center", "alpha", "coeff", "norm", "lmn")}, *grid_params(g))
+    idx = g["idx"]
+    xyz, w, wb = o.grid()
+    assert np.array_equal(xyz[idx], g["pts"])
+    assert np.array_equal(wb[idx], g["wb"]) and np.array_equal(w[idx], g["w"])  # same libm, same operation order
+    assert np.max(np.abs(o.amplitudes()[idx] - g["phi"])) <= 1e-15
+    raw = o.set_density(g["P"], correct=True)
+    assert abs(raw - float(g["nel_raw"])) <= 1e-11 * abs(raw)
+    rho = o.densities()[idx]
+    assert np.max(np.abs(rho - g["rho"])) <= 1e-13 * np.max(g["rho"])
+    J, hi = o.hartree()
+    XC, exc = o.xc()
+    assert np.max(np.abs(hi["rho_lm"][:, g["rad_idx"]] - g["rho_lm"])) <= 1e-12 * np.max(np.abs(g["rho_lm"]))
+    assert np.max(np.abs(hi["U_lm"][:, g["rad_idx"]] - g["U_lm"])) <= 1e-10 * np.max(np.abs(g["U_lm"]))
+    assert np.max(np.abs(hi["V"][idx] - g["V"])) <= 1e-11 * np.max(np.abs(g["V"]))
+    assert np.max(np.abs(J - g["J"])) <= 1e-11
+    assert np.max(np.abs(XC - g["XC"])) <= 1e-12
+    assert abs(exc - float(g["exc"])) <= 1e-11
+    o.close()

@@ -216,3 +216,39 @@ def test_error_paths():
     with pytest.raises(GridError):
         mb.create_grid()  # f-type function: "Undefined orbital type" (src/cgf.cpp:227-230)
     mg.close()
+
+
+@pytest.mark.parametrize("nwater,grid", [(2, (10, 4, 5)), (3, (15, 7, 8))])
+def test_against_c_restatement_on_seeded_clusters(nwater, grid):
+    """Fresh inputs that are in no fixture: synthetic water clusters, CUDA path vs oracle/oracle_port.c (same seeds)."""
+    from oracle import portpy
+
+    if not portpy.available():
+        pytest.skip("oracle/liboracle.so not built")
+    from dftcxx_b200.grid import MolecularGrid
+    from dftcxx_b200.systems import synthetic_density, water_cluster
+
+    mol = water_cluster(nwater)
+    s = {k: getattr(mol, k) for k in ("Z", "xyz", "bf_nprim", "bf_center", "alpha", "coeff", "norm", "lmn")}
+    o = portpy.Port(s, *grid)
+    mg = MolecularGrid(mol)
+    mg.set_grid_parameters(*grid)
+    mg.create_grid()
+    try:
+        xyz, w, wb = o.grid()
+        assert np.array_equal(mg.get_positions(), xyz)
+        assert relerr(mg.get_becke_weights(), wb, BECKE_FLOOR) <= TOL_REL
+        assert np.max(np.abs(mg.get_amplitudes() - o.amplitudes())) <= 1e-13
+        for seed in (1, 2):
+            P = synthetic_density(mol, seed=seed)
+            o.set_density(P)
+            Jo, hi = o.hartree()
+            XCo, exco = o.xc()
+            J, XC, exc, nel = mg.iteration(P)
+            assert relerr(mg.get_densities(), o.densities(), 1e-6 * np.max(o.densities())) <= TOL_REL
+            assert np.max(np.abs(J - Jo)) <= TOL_MATRIX_ABS and np.max(np.abs(XC - XCo)) <= TOL_MATRIX_ABS
+            assert abs(exc - exco) <= 1e-10 and abs(nel - o.electron_count()) <= 1e-10
+            assert np.max(np.abs(mg.get_potential() - hi["V"])) <= 1e-11 * np.max(np.abs(hi["V"]))
+    finally:
+        mg.close()
+        o.close()
