@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -90,13 +91,15 @@ struct dftgrid {
     LdaConstants lda{};
     DevBuf<double> d_center_xyz, d_exp_alpha, d_prim_coeff, d_prim_norm;
     DevBuf<int> d_bf_center, d_bf_prim_off, d_center_exp_off, d_prim_exp, d_prim_lmn;
+    DevBuf<PhiPrim> d_prims;
 
     // device: per point
     DevBuf<double> d_x, d_y, d_z, d_w, d_wb, d_rho, d_dxc, d_exw, d_V, d_Vown, d_dJ, d_phi;
     // device: per iteration
     DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
-    DevBuf<int> d_pairs;
-    int npairs = 0, nsplit = 1;
+    DevBuf<int> d_pairs, d_cta_off, d_item_off;
+    DevBuf<ConSeg> d_segs;
+    int npairs = 0, nsplit = 1, con_ctas = 1;
 
     // pinned staging
     double* h_P = nullptr;
@@ -309,10 +312,65 @@ void do_build(dftgrid* h) {
     h->d_pairs.upload(pairs, st);
     int nsm = 148;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
-    const long nchunk = (g.nloc + kTileK - 1) / kTileK;
-    long want = std::max<long>(1, (2L * nsm + 2L * h->npairs - 1) / (2L * h->npairs));  // ~2 waves of CTAs over both matrices
-    h->nsplit = (int)std::max<long>(1, std::min<long>(want, nchunk));
-    h->d_partial.alloc((size_t)2 * h->npairs * h->nsplit * kTileM * kTileN);
+    {
+        // stream-K schedule of the [XC | J] contraction: equal DMMA cost per CTA, one CTA per SM
+        const long nchunk = (g.nloc + kTileK - 1) / kTileK;
+        const int nitems = 2 * h->npairs;
+        std::vector<int> cost(nitems);
+        long W = 0;
+        for (int it = 0; it < nitems; it++) {
+            const int tj = pairs[2 * (it % h->npairs) + 1];
+            const char* nc = std::getenv("DFTGRID_NARROW_COST");  // cost of a 64-wide edge tile relative to 10 for a full one
+            cost[it] = std::min(kTileN, h->nbp - tj * kTileN) <= 64 ? (nc ? std::atoi(nc) : 6) : 10;
+            W += (long)cost[it] * nchunk;
+        }
+        const int G = (int)std::max<long>(1, std::min<long>(nsm, W / 20 > 0 ? W / 20 : 1));
+        std::vector<ConSeg> segs;
+        std::vector<int> cta_off(1, 0), item_off(nitems + 1, 0);
+        int item = 0;
+        long cpos = 0;  // next unassigned chunk of `item`
+        long done = 0;  // cost units assigned so far
+        for (int c = 0; c < G; c++) {
+            const long target = W * (c + 1) / G;  // cumulative cost this CTA should reach
+            while (item < nitems && (done < target || c == G - 1)) {
+                long take = (target - done + cost[item] - 1) / cost[item];
+                if (c == G - 1) take = nchunk - cpos;
+                take = std::min(take, nchunk - cpos);
+                if (take > 0) {
+                    segs.push_back(ConSeg{item / h->npairs, item % h->npairs, (int)cpos, (int)(cpos + take)});
+                    cpos += take;
+                    done += take * cost[item];
+                }
+                if (cpos == nchunk) {
+                    item++;
+                    cpos = 0;
+                    item_off[item] = (int)segs.size();
+                } else if (c != G - 1) {
+                    break;
+                }
+            }
+            cta_off.push_back((int)segs.size());
+        }
+        for (int it = item + 1; it <= nitems; it++) item_off[it] = (int)segs.size();
+        if (nchunk == 0) {  // empty shard: every item still gets one (empty) segment so that the reduction writes zeros
+            segs.clear();
+            cta_off.assign(1, 0);
+            for (int it = 0; it < nitems; it++) {
+                item_off[it] = it;
+                segs.push_back(ConSeg{it / h->npairs, it % h->npairs, 0, 0});
+            }
+            item_off[nitems] = nitems;
+            cta_off.push_back(nitems);
+        }
+        h->con_ctas = (int)cta_off.size() - 1;
+        h->nsplit = (int)segs.size();
+        h->d_segs.alloc(segs.size());
+        CK(cudaMemcpyAsync(h->d_segs.p, segs.data(), segs.size() * sizeof(ConSeg), cudaMemcpyHostToDevice, st));
+        h->d_cta_off.upload(cta_off, st);
+        h->d_item_off.upload(item_off, st);
+        h->d_partial.alloc((size_t)segs.size() * kTileM * kTileN);
+        CK(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+    }
 
     if (!h->h_P) CK(cudaMallocHost(&h->h_P, sizeof(double) * std::max<size_t>(1, (size_t)h->nbf * h->nbf)));
     if (!h->h_res) CK(cudaMallocHost(&h->h_res, sizeof(double) * ((size_t)2 * h->nbf * h->nbf + 2)));
@@ -340,8 +398,11 @@ void do_build(dftgrid* h) {
     }
     record(h, 2);
     if (g.nloc > 0) {
-        PhiBasis B{h->nbf, h->nbp, h->d_bf_center.p, h->d_bf_prim_off.p, h->d_center_exp_off.p, h->d_exp_alpha.p,
-                   h->d_prim_exp.p, h->d_prim_coeff.p, h->d_prim_norm.p, h->d_prim_lmn.p, h->d_center_xyz.p};
+        std::vector<PhiPrim> prims(h->prim_coeff.size());
+        for (size_t k = 0; k < prims.size(); k++) prims[k] = PhiPrim{h->prim_coeff[k], h->prim_norm[k], h->prim_exp[k], h->prim_lmn[k], {0, 0}};
+        h->d_prims.alloc(prims.size());
+        CK(cudaMemcpyAsync(h->d_prims.p, prims.data(), prims.size() * sizeof(PhiPrim), cudaMemcpyHostToDevice, st));
+        PhiBasis B{h->nbf, h->nbp, h->d_bf_center.p, h->d_bf_prim_off.p, h->d_center_exp_off.p, h->d_exp_alpha.p, h->d_prims.p, h->d_center_xyz.p};
         const size_t smem = ((size_t)kPhiPts * (kPhiCols + 1) + (size_t)kPhiMaxExp * kPhiPts) * sizeof(double);
         k_phi<<<(unsigned)((g.nloc + kPhiPts - 1) / kPhiPts), kPhiPts, smem, st>>>(g.nloc, B, h->d_x.p, h->d_y.p, h->d_z.p, h->d_phi.p);
         h->launches++;
@@ -420,8 +481,23 @@ void run_potential(dftgrid* h) {
     record(h, 10);
     if (g.nloc > 0) {
         const size_t smem = ((size_t)g.nrad + (size_t)(g.lmax + 1) * (g.lmax + 1) + 2 * g.lmax + 2) * sizeof(double);
-        k_interp<<<(unsigned)((g.nloc + 127) / 128), 128, smem, st>>>(g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p, h->d_Vown.p,
-                                                                      h->d_xs.p, h->d_pre.p, h->d_coef.p, h->d_V.p, h->d_dJ.p);
+        const unsigned blocks = (unsigned)((g.nloc + 127) / 128);
+#define DFG_INTERP_ARGS g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p, h->d_Vown.p, h->d_xs.p, h->d_pre.p, h->d_coef.p, h->d_V.p, h->d_dJ.p
+        const char* var = std::getenv("DFTGRID_INTERP_VARIANT");
+        const int variant = var ? std::atoi(var) : 0;
+        switch (g.lmax) {  // unrolled kernels for the reference's grid presets (src/settings.cpp:158-187), generic otherwise
+            case 5: k_interp_t<5, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
+            case 8: k_interp_t<8, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
+            case 10:
+                if (variant == 1) k_interp_t<10, 4><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS);
+                else if (variant == 2) k_interp_t<10, 3><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS);
+                else if (variant == 3) k_interp_t<10, 8><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS);
+                else k_interp_t<10, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS);
+                break;
+            case 11: k_interp_t<11, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
+            default: k_interp<<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
+        }
+#undef DFG_INTERP_ARGS
         h->launches++;
     }
     record(h, 11);
@@ -434,9 +510,9 @@ void run_contract(dftgrid* h) {
     const GridShape& g = h->g;
     const size_t nb2 = (size_t)h->nbf * h->nbf;
     record(h, 12);
-    dim3 grid(h->npairs, h->nsplit, 2);
-    k_contract<<<grid, kDenseThreads, kConSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_pairs.p, h->d_partial.p, g.nloc, h->nbp, h->nsplit);
-    k_contract_reduce<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->npairs, h->nsplit, h->nbf, 1.0, 0.5,
+    k_contract<<<h->con_ctas, kDenseThreads, kConSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_pairs.p, h->d_segs.p, h->d_cta_off.p,
+                                                                  h->d_partial.p, g.nloc, h->nbp);
+    k_contract_reduce<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 0.5,
                                                          h->d_res.p + nb2, h->d_res.p);
     h->launches += 2;
     // exc and nel come from the already-reduced shell sums (identical on every rank): appended after the reduced block

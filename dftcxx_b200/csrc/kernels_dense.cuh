@@ -85,6 +85,26 @@ __device__ __forceinline__ void rho_mma_stage(const double* st, double (&acc)[4]
     }
 }
 
+// Schedule of one CTA's (column slab, k-chunk) steps.  P is symmetric, so for column slab J only the k-chunks at or
+// beyond the slab are visited: first the chunks past the slab's end (their contribution counts twice: P[n][k] and
+// P[k][n]), then — after doubling the accumulators, which is exact — the chunks inside the slab.  This halves the
+// DMMA work of rho = 2 sum_n phi_n (sum_k P_nk phi_k) relative to the full product.
+struct RhoStep {
+    int slab, i, nbp;
+    __device__ __forceinline__ int nk() const { return nbp / kTileK; }
+    __device__ __forceinline__ int first_chunk() const { return slab * (kTileN / kTileK); }
+    __device__ __forceinline__ int end_chunk() const { return min(nk(), (slab + 1) * (kTileN / kTileK)); }
+    __device__ __forceinline__ int count() const { return nk() - first_chunk(); }
+    __device__ __forceinline__ int outer() const { return nk() - end_chunk(); }  // chunks past the slab
+    __device__ __forceinline__ int chunk() const { return i < outer() ? end_chunk() + i : first_chunk() + (i - outer()); }
+    __device__ __forceinline__ void advance() {
+        if (++i == count()) {
+            i = 0;
+            slab++;
+        }
+    }
+};
+
 // grid.x = ceil(nloc/128); P is the zero-padded [nbp][nbp] density matrix (symmetric).
 __global__ void __launch_bounds__(kDenseThreads, 1)
 k_rho(const double* __restrict__ phi, const double* __restrict__ P, double* __restrict__ rho, long nloc, int nbp) {
@@ -96,41 +116,53 @@ k_rho(const double* __restrict__ phi, const double* __restrict__ P, double* __re
     const long p0 = (long)blockIdx.x * kTileM;
     const int nk = nbp / kTileK;
     const int nslab = (nbp + kTileN - 1) / kTileN;
-    const int total = nslab * nk;
+    int total = 0;
+    for (int J = 0; J < nslab; J++) total += nk - J * (kTileN / kTileK);
 
     double rowsum[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][8][2];
 
-    // prologue
+    RhoStep ld{0, 0, nbp}, cs{0, 0, nbp};
     for (int s = 0; s < kStages - 1; s++) {
-        if (s < total) rho_load_stage(sm + (size_t)s * kRhoStageDoubles, phi, P, p0, nloc, nbp, (s / nk) * kTileN, (s % nk) * kTileK);
+        if (s < total) {
+            rho_load_stage(sm + (size_t)s * kRhoStageDoubles, phi, P, p0, nloc, nbp, ld.slab * kTileN, ld.chunk() * kTileK);
+            ld.advance();
+        }
         cp_async_commit();
     }
     for (int it = 0; it < total; it++) {
-        const int slab = (it / nk) * kTileN, kci = it % nk;
+        const int slab = cs.slab * kTileN;
         const int ncols = min(kTileN, nbp - slab);  // 32, 64, 96 or 128
         const bool narrow = ncols <= 64;            // 8 warps as 4 x 2 over [128 x 64]: 4 n-tiles per warp
-        if (kci == 0) {
+        if (cs.i == 0) {
 #pragma unroll
             for (int mt = 0; mt < 4; mt++)
 #pragma unroll
                 for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
         }
+        if (cs.i == cs.outer()) {  // entering the slab's own k-range: everything so far is an off-diagonal block
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {
+                    acc[mt][nt][0] *= 2.0;
+                    acc[mt][nt][1] *= 2.0;
+                }
+        }
         cp_async_wait<kStages - 2>();
         __syncthreads();
-        {
-            const int nx = it + kStages - 1;
-            if (nx < total)
-                rho_load_stage(sm + (size_t)(nx % kStages) * kRhoStageDoubles, phi, P, p0, nloc, nbp, (nx / nk) * kTileN, (nx % nk) * kTileK);
-            cp_async_commit();
+        if (it + kStages - 1 < total) {
+            rho_load_stage(sm + (size_t)((it + kStages - 1) % kStages) * kRhoStageDoubles, phi, P, p0, nloc, nbp, ld.slab * kTileN, ld.chunk() * kTileK);
+            ld.advance();
         }
+        cp_async_commit();
         const double* st = sm + (size_t)(it % kStages) * kRhoStageDoubles;
         if (narrow)
             rho_mma_stage<4>(st, acc, wm, wn, lane);
         else
             rho_mma_stage<8>(st, acc, wm, wn, lane);
-        if (kci == nk - 1) {
-            // epilogue of this column slab: rowsum += T[p][n] * Phi[p][n]
+        if (cs.i == cs.count() - 1) {
+            // epilogue of this column slab: rowsum += T'[p][n] * Phi[p][n]
             const int ntn = narrow ? 4 : 8;
 #pragma unroll
             for (int mt = 0; mt < 4; mt++) {
@@ -150,6 +182,7 @@ k_rho(const double* __restrict__ phi, const double* __restrict__ P, double* __re
                 }
             }
         }
+        cs.advance();
     }
     cp_async_wait<0>();
     // reduce over the 4 lanes of a quad, then over the two N-warps
@@ -220,75 +253,85 @@ __device__ __forceinline__ void con_mma_stage(const double* st, bool diag, doubl
     }
 }
 
-// grid = (npairs, nsplit, 2).  pair_ij[2*pair] = (ti, tj) with ti <= tj.  d0/d1: per-point weights of matrix 0/1
-// (the odd point of a half-filled last chunk is covered by zero padding of d).  partial: [2][npairs][nsplit][128*128].
+// Work decomposition ("stream-K"): the (matrix z, tile pair) items, each nchunk k-chunks long and weighted by their
+// DMMA cost (a 64-wide edge tile costs half), are laid end to end and cut into one equal share per CTA (one CTA per
+// SM).  A CTA therefore executes 1-3 segments = (z, pair, [c_begin, c_end)) and writes one partial tile per segment;
+// k_contract_reduce adds an item's partial tiles in a fixed order.  The schedule is built on the host (dftgrid_api.cu).
+struct ConSeg {
+    int z, pair, c_begin, c_end;
+};
+
+// grid = number of CTAs in the schedule.  d0/d1: per-point weights of matrix 0/1 (zero-padded past the shard).
+// partial: [nseg][128*128].
 __global__ void __launch_bounds__(kDenseThreads, 1)
 k_contract(const double* __restrict__ phi, const double* __restrict__ d0, const double* __restrict__ d1,
-           const int* __restrict__ pair_ij, double* __restrict__ partial, long nloc, int nbp, int nsplit) {
+           const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs, const int* __restrict__ cta_seg_off,
+           double* __restrict__ partial, long nloc, int nbp) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp & 3, wn = warp >> 2;
     const int g = lane >> 2, q = lane & 3;
-    const int pair = blockIdx.x, split = blockIdx.y, z = blockIdx.z;
-    const int ti = pair_ij[2 * pair], tj = pair_ij[2 * pair + 1];
-    const int ci = ti * kTileM, cj = tj * kTileN;
-    const bool diag = ti == tj;
-    const double* d = z == 0 ? d0 : d1;
-    const long nchunk = (nloc + kTileK - 1) / kTileK;
-    const long c_begin = nchunk * split / nsplit, c_end = nchunk * (split + 1) / nsplit;
-    const int total = (int)(c_end - c_begin);
-    const int ncols = min(kTileN, nbp - cj);
-    const bool narrow = ncols <= 64;
+    const int s_begin = cta_seg_off[blockIdx.x], s_end = cta_seg_off[blockIdx.x + 1];
+    for (int sidx = s_begin; sidx < s_end; sidx++) {
+        const ConSeg sg = segs[sidx];
+        const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
+        const int ci = ti * kTileM, cj = tj * kTileN;
+        const bool diag = ti == tj;
+        const double* d = sg.z == 0 ? d0 : d1;
+        const long c_begin = sg.c_begin;
+        const int total = sg.c_end - sg.c_begin;
+        const bool narrow = min(kTileN, nbp - cj) <= 64;
 
-    double acc[4][8][2];
+        double acc[4][8][2];
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++)
+        for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    for (int s = 0; s < kStages - 1; s++) {
-        if (s < total) con_load_stage(sm + (size_t)s * kConStageDoubles, phi, d, (c_begin + s) * kTileK, nloc, nbp, ci, cj, diag);
-        cp_async_commit();
-    }
-    for (int it = 0; it < total; it++) {
-        cp_async_wait<kStages - 2>();
-        __syncthreads();
-        {
-            const int nx = it + kStages - 1;
-            if (nx < total)
-                con_load_stage(sm + (size_t)(nx % kStages) * kConStageDoubles, phi, d, (c_begin + nx) * kTileK, nloc, nbp, ci, cj, diag);
+        for (int s = 0; s < kStages - 1; s++) {
+            if (s < total) con_load_stage(sm + (size_t)s * kConStageDoubles, phi, d, (c_begin + s) * kTileK, nloc, nbp, ci, cj, diag);
             cp_async_commit();
         }
-        const double* st = sm + (size_t)(it % kStages) * kConStageDoubles;
-        if (narrow)
-            con_mma_stage<4>(st, diag, acc, wm, wn, lane);
-        else
-            con_mma_stage<8>(st, diag, acc, wm, wn, lane);
-    }
-    cp_async_wait<0>();
-    double* out = partial + (((size_t)z * gridDim.x + pair) * nsplit + split) * (size_t)(kTileM * kTileN);
-    const int ntn = narrow ? 4 : 8;
-#pragma unroll
-    for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
-            const int r = wm * 32 + mt * 8 + g;
-            if (nt < ntn) {
-                const int c = wn * (ntn * 8) + nt * 8 + q * 2;
-                *reinterpret_cast<double2*>(out + r * kTileN + c) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-            } else if (narrow) {
-                const int c = 64 + wn * 32 + (nt - 4) * 8 + q * 2;
-                *reinterpret_cast<double2*>(out + r * kTileN + c) = make_double2(0.0, 0.0);
+        for (int it = 0; it < total; it++) {
+            cp_async_wait<kStages - 2>();
+            __syncthreads();
+            {
+                const int nx = it + kStages - 1;
+                if (nx < total)
+                    con_load_stage(sm + (size_t)(nx % kStages) * kConStageDoubles, phi, d, (c_begin + nx) * kTileK, nloc, nbp, ci, cj, diag);
+                cp_async_commit();
             }
+            const double* st = sm + (size_t)(it % kStages) * kConStageDoubles;
+            if (narrow)
+                con_mma_stage<4>(st, diag, acc, wm, wn, lane);
+            else
+                con_mma_stage<8>(st, diag, acc, wm, wn, lane);
         }
+        cp_async_wait<0>();
+        __syncthreads();  // every warp is done with the stage buffers before the next segment refills them
+        double* out = partial + (size_t)sidx * (size_t)(kTileM * kTileN);
+        const int ntn = narrow ? 4 : 8;
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                const int r = wm * 32 + mt * 8 + g;
+                if (nt < ntn) {
+                    const int c = wn * (ntn * 8) + nt * 8 + q * 2;
+                    *reinterpret_cast<double2*>(out + r * kTileN + c) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                }
+            }
+    }
 }
 
-// out0/out1: nb x nb (symmetric => row/column-major agnostic).  Each thread sums one element over the splits in order.
-__global__ void k_contract_reduce(const double* __restrict__ partial, const int* __restrict__ pair_ij, int npairs, int nsplit,
-                                  int nb, double scale0, double scale1, double* __restrict__ out0, double* __restrict__ out1) {
+// out0/out1: nb x nb (symmetric => row/column-major agnostic).  Each thread sums one element over the item's partial
+// tiles [item_slot_off[item], item_slot_off[item+1]) in order.  grid = (npairs, 2).
+__global__ void k_contract_reduce(const double* __restrict__ partial, const int* __restrict__ pair_ij, const int* __restrict__ item_slot_off,
+                                  int npairs, int nb, int nbp, double scale0, double scale1, double* __restrict__ out0, double* __restrict__ out1) {
     const int pair = blockIdx.x, z = blockIdx.y;
     const int ti = pair_ij[2 * pair], tj = pair_ij[2 * pair + 1];
-    const double* base = partial + ((size_t)z * npairs + pair) * nsplit * (size_t)(kTileM * kTileN);
+    const int item = z * npairs + pair;
+    const int k0 = item_slot_off[item], k1 = item_slot_off[item + 1];
     double* out = z == 0 ? out0 : out1;
     const double scale = z == 0 ? scale0 : scale1;
     for (int e = threadIdx.x; e < kTileM * kTileN; e += blockDim.x) {
@@ -297,7 +340,7 @@ __global__ void k_contract_reduce(const double* __restrict__ partial, const int*
         if (gi >= nb || gj >= nb) continue;
         if (ti == tj && gj < gi) continue;  // lower part of a diagonal tile is the mirror image
         double s = 0.0;
-        for (int k = 0; k < nsplit; k++) s += base[(size_t)k * (kTileM * kTileN) + e];
+        for (int k = k0; k < k1; k++) s += partial[(size_t)k * (kTileM * kTileN) + e];
         s *= scale;
         out[(size_t)gi * nb + gj] = s;
         out[(size_t)gj * nb + gi] = s;

@@ -99,20 +99,24 @@ k_becke(GridShape g, const double* __restrict__ atom_xyz, const double* __restri
 // A [kPhiPts x kPhiCols] tile is staged in shared memory so that every Phi row is written with full 256-byte
 // coalesced segments; pad columns [nbf, nbp) are written as zeros.
 constexpr int kPhiPts = 128;
-constexpr int kPhiCols = 64;
-constexpr int kPhiMaxExp = 40;
+constexpr int kPhiCols = 32;    // one 256-byte row segment per point and pass
+constexpr int kPhiMaxExp = 24;  // distinct exponents on one centre (STO-6G third row needs 18)
+
+struct PhiPrim {  // one primitive term, 32 bytes = two 128-bit loads
+    double coeff, norm;
+    int exp_idx;  // absolute index into exp_alpha
+    int lmn;      // l | m<<4 | n<<8
+    int pad[2];
+};
 
 struct PhiBasis {
     int nbf, nbp;
-    const int* bf_atom;       // [nbf] atom of column b
+    const int* bf_atom;       // [nbf] centre of column b
     const int* bf_prim_off;   // [nbf+1]
-    const int* atom_exp_off;  // [natoms+1]
-    const double* exp_alpha;  // distinct exponents, atom after atom
-    const int* prim_exp;      // [nprim] absolute index into exp_alpha
-    const double* prim_coeff;
-    const double* prim_norm;
-    const int* prim_lmn;      // l | m<<4 | n<<8
-    const double* atom_xyz;
+    const int* atom_exp_off;  // [ncentres+1]
+    const double* exp_alpha;  // distinct exponents, centre after centre
+    const PhiPrim* prims;     // [nprim]
+    const double* atom_xyz;   // [ncentres][3]
 };
 
 __device__ __forceinline__ double ipow_rn(double acc, double x, int n) {
@@ -122,7 +126,7 @@ __device__ __forceinline__ double ipow_rn(double acc, double x, int n) {
     return acc;
 }
 
-__global__ void __launch_bounds__(kPhiPts)
+__global__ void __launch_bounds__(kPhiPts, 3)
 k_phi(long nloc, PhiBasis B, const double* __restrict__ px, const double* __restrict__ py,
       const double* __restrict__ pz, double* __restrict__ phi) {
     extern __shared__ double sm[];
@@ -133,36 +137,37 @@ k_phi(long nloc, PhiBasis B, const double* __restrict__ px, const double* __rest
     const long p = p0 + tid;
     const bool live = p < nloc;
     const double x = live ? px[p] : 0.0, y = live ? py[p] : 0.0, z = live ? pz[p] : 0.0;
-    int cur_atom = -1;
+    int cur_atom = -1, e0 = 0;
     double dx = 0, dy = 0, dz = 0;
     for (int c0 = 0; c0 < B.nbp; c0 += kPhiCols) {
         const int c1 = min(c0 + kPhiCols, B.nbp);
         for (int b = c0; b < c1; b++) {
             double val = 0.0;
             if (b < B.nbf) {
-                const int atom = B.bf_atom[b];
+                const int atom = __ldg(B.bf_atom + b);
                 if (atom != cur_atom) {
                     cur_atom = atom;
-                    dx = __dsub_rn(x, B.atom_xyz[3 * atom]);
-                    dy = __dsub_rn(y, B.atom_xyz[3 * atom + 1]);
-                    dz = __dsub_rn(z, B.atom_xyz[3 * atom + 2]);
+                    dx = __dsub_rn(x, __ldg(B.atom_xyz + 3 * atom));
+                    dy = __dsub_rn(y, __ldg(B.atom_xyz + 3 * atom + 1));
+                    dz = __dsub_rn(z, __ldg(B.atom_xyz + 3 * atom + 2));
                     const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                    const int e0 = B.atom_exp_off[atom], e1 = B.atom_exp_off[atom + 1];
+                    e0 = __ldg(B.atom_exp_off + atom);
+                    const int e1 = __ldg(B.atom_exp_off + atom + 1);
                     for (int u = e0; u < e1; u++) {
-                        const double arg = __dmul_rn(B.exp_alpha[u], r2);
+                        const double arg = __dmul_rn(__ldg(B.exp_alpha + u), r2);
                         ex[(size_t)(u - e0) * kPhiPts + tid] = arg > 746.0 ? 0.0 : exp(-arg);
                     }
                 }
-                const int e0 = B.atom_exp_off[atom];
-                const int k0 = B.bf_prim_off[b], k1 = B.bf_prim_off[b + 1];
+                const int k0 = __ldg(B.bf_prim_off + b), k1 = __ldg(B.bf_prim_off + b + 1);
                 for (int k = k0; k < k1; k++) {
-                    const int lmn = B.prim_lmn[k];
-                    double a = B.prim_norm[k];
-                    a = ipow_rn(a, dx, lmn & 15);
-                    a = ipow_rn(a, dy, (lmn >> 4) & 15);
-                    a = ipow_rn(a, dz, (lmn >> 8) & 15);
-                    a = __dmul_rn(a, ex[(size_t)(B.prim_exp[k] - e0) * kPhiPts + tid]);
-                    val = __dadd_rn(val, __dmul_rn(B.prim_coeff[k], a));
+                    const double2 cn = __ldg(reinterpret_cast<const double2*>(B.prims + k));
+                    const int2 il = __ldg(reinterpret_cast<const int2*>(B.prims + k) + 2);
+                    double a = cn.y;
+                    a = ipow_rn(a, dx, il.y & 15);
+                    a = ipow_rn(a, dy, (il.y >> 4) & 15);
+                    a = ipow_rn(a, dz, (il.y >> 8) & 15);
+                    a = __dmul_rn(a, ex[(size_t)(il.x - e0) * kPhiPts + tid]);
+                    val = __dadd_rn(val, __dmul_rn(cn.x, a));
                 }
             }
             tile[(size_t)tid * (kPhiCols + 1) + (b - c0)] = val;
@@ -172,7 +177,8 @@ k_phi(long nloc, PhiBasis B, const double* __restrict__ px, const double* __rest
         for (int row = tid >> 5; row < kPhiPts; row += kPhiPts / 32) {
             const long pr = p0 + row;
             if (pr >= nloc) break;
-            for (int c = tid & 31; c < ncol; c += 32) phi[pr * B.nbp + c0 + c] = tile[(size_t)row * (kPhiCols + 1) + c];
+            const int c = tid & 31;
+            if (c < ncol) phi[pr * B.nbp + c0 + c] = tile[(size_t)row * (kPhiCols + 1) + c];
         }
         __syncthreads();
     }

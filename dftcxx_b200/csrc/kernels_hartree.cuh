@@ -347,4 +347,104 @@ k_interp(GridShape g, const double* __restrict__ atom_xyz, const double* __restr
     dJ[p] = w[p] * Vacc;
 }
 
+// Fully unrolled variant for a compile-time lmax (the presets use 5, 8, 10, 11): all (l, m) loop indices, recurrence
+// constants and table offsets become immediates, which removes the integer/convert/branch overhead that dominates the
+// generic kernel (about 30 instructions per (l,m) term there).  Same arithmetic, same accumulation order.
+template <int L, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ px, const double* __restrict__ py,
+           const double* __restrict__ pz, const double* __restrict__ w, const double* __restrict__ Vown,
+           const double* __restrict__ xs, const double* __restrict__ pre, const double* __restrict__ coef,
+           double* __restrict__ V, double* __restrict__ dJ) {
+    extern __shared__ double sm[];
+    const int N = g.nrad;
+    constexpr int NLM = (L + 1) * (L + 1);
+    double* xsh = sm;        // [N]
+    double* presh = sm + N;  // [(L+1)^2]
+    for (int i = threadIdx.x; i < N; i += blockDim.x) xsh[i] = xs[i];
+    for (int i = threadIdx.x; i < (L + 1) * (L + 1); i += blockDim.x) presh[i] = pre[i];
+    __syncthreads();
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.nloc) return;
+    const int own = (int)((g.shell0 + p / g.nang) / g.nrad);
+    const double x = px[p], y = py[p], z = pz[p];
+    double Vacc = 0.0;
+    for (int k = 0; k < g.natoms; k++) {
+        if (k == own) {
+            Vacc += Vown[p];
+            continue;
+        }
+        const double dx = x - atom_xyz[3 * k], dy = y - atom_xyz[3 * k + 1], dz = z - atom_xyz[3 * k + 2];
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);
+        const double rinv = 1.0 / r;
+        int iv;
+        double tt;
+        if (r < xsh[0]) {
+            iv = 0;
+            tt = 0.0;
+        } else if (r >= xsh[N - 1]) {
+            iv = N - 1;
+            tt = 0.0;
+        } else {
+            int lo_ = 0, hi_ = N - 1;  // x[lo_] < r <= x[hi_] (or r == x[0]): first i with r <= x_i
+            while (hi_ - lo_ > 1) {
+                const int mid = (lo_ + hi_) >> 1;
+                if (r <= xsh[mid])
+                    hi_ = mid;
+                else
+                    lo_ = mid;
+            }
+            iv = hi_ - 1;
+            tt = r - xsh[iv];
+        }
+        const double4* cf = reinterpret_cast<const double4*>(coef + ((size_t)k * N + iv) * NLM * 4);
+        const double tt2 = tt * tt, tt3 = tt2 * tt;
+        const double ct = dz / r;
+        const double st = sqrt(1.0 - ct * ct);
+        const double rxy = sqrt(dx * dx + dy * dy);
+        double c1 = 1.0, s1 = 0.0;
+        if (rxy > 0.0) {
+            c1 = dx / rxy;
+            s1 = dy / rxy;
+        }
+        double cm = 1.0, sn = 0.0, pmm = 1.0, sum = 0.0;
+#pragma unroll
+        for (int m = 0; m <= L; m++) {
+            if (m > 0) {
+                pmm *= -(double)(2 * m - 1) * st;
+                const double cn = cm * c1 - sn * s1;
+                sn = sn * c1 + cm * s1;
+                cm = cn;
+            }
+            double pl2 = 0.0, pl1 = pmm;
+#pragma unroll
+            for (int l = m; l <= L; l++) {
+                double pl;
+                if (l == m)
+                    pl = pmm;
+                else if (l == m + 1)
+                    pl = ct * (double)(2 * m + 1) * pmm;
+                else
+                    pl = ((double)(2 * l - 1) * ct * pl1 + (double)(-l - m + 1) * pl2) * (1.0 / (double)(l - m));
+                pl2 = pl1;
+                pl1 = pl;
+                const double pf = presh[l * (L + 1) + m] * rinv;
+                {
+                    const double4 c = cf[l * l + l + m];
+                    const double sv = c.x + c.y * tt + c.z * tt2 + c.w * tt3;
+                    sum += pf * (pl * cm) * sv;
+                }
+                if (m > 0) {
+                    const double4 c = cf[l * l + l - m];
+                    const double sv = c.x + c.y * tt + c.z * tt2 + c.w * tt3;
+                    sum += pf * (pl * sn) * sv;
+                }
+            }
+        }
+        Vacc += sum;
+    }
+    V[p] = Vacc;
+    dJ[p] = w[p] * Vacc;
+}
+
 }  // namespace dfg
