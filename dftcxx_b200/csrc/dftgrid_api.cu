@@ -92,6 +92,8 @@ struct dftgrid {
     DevBuf<double> d_center_xyz, d_exp_alpha, d_prim_coeff, d_prim_norm;
     DevBuf<int> d_bf_center, d_bf_prim_off, d_center_exp_off, d_prim_exp, d_prim_lmn;
     DevBuf<PhiPrim> d_prims;
+    DevBuf<PhiShell> d_shells;
+    DevBuf<int> d_pass_rng;
 
     // device: per point
     DevBuf<double> d_x, d_y, d_z, d_w, d_wb, d_rho, d_dxc, d_exw, d_V, d_Vown, d_dJ, d_phi;
@@ -398,11 +400,76 @@ void do_build(dftgrid* h) {
     }
     record(h, 2);
     if (g.nloc > 0) {
-        std::vector<PhiPrim> prims(h->prim_coeff.size());
-        for (size_t k = 0; k < prims.size(); k++) prims[k] = PhiPrim{h->prim_coeff[k], h->prim_norm[k], h->prim_exp[k], h->prim_lmn[k], {0, 0}};
+        // group the columns into shells (see kernels_grid.cuh): S / P / D runs that share their primitives, else generic
+        std::vector<PhiShell> shells;
+        std::vector<PhiPrim> prims;
+        auto slot_of = [&](int k, int centre) { return h->prim_exp[k] - h->center_exp_off[centre]; };
+        auto same_prims = [&](int b0, int b1) {  // same centre, exponents and coefficients
+            if (h->bf_center[b0] != h->bf_center[b1]) return false;
+            const int n0 = h->bf_prim_off[b0 + 1] - h->bf_prim_off[b0], n1 = h->bf_prim_off[b1 + 1] - h->bf_prim_off[b1];
+            if (n0 != n1) return false;
+            for (int k = 0; k < n0; k++) {
+                const int k0 = h->bf_prim_off[b0] + k, k1 = h->bf_prim_off[b1] + k;
+                if (h->prim_exp[k0] != h->prim_exp[k1] || h->prim_coeff[k0] != h->prim_coeff[k1]) return false;
+            }
+            return true;
+        };
+        auto all_lmn = [&](int b, int code) {
+            for (int k = h->bf_prim_off[b]; k < h->bf_prim_off[b + 1]; k++)
+                if (h->prim_lmn[k] != code) return false;
+            return true;
+        };
+        auto same_norms = [&](int b0, int b1) {
+            const int n = h->bf_prim_off[b0 + 1] - h->bf_prim_off[b0];
+            for (int k = 0; k < n; k++)
+                if (h->prim_norm[h->bf_prim_off[b0] + k] != h->prim_norm[h->bf_prim_off[b1] + k]) return false;
+            return true;
+        };
+        const int LX = 1, LY = 1 << 4, LZ = 1 << 8;
+        for (int b = 0; b < h->nbf;) {
+            const int centre = h->bf_center[b], k0 = h->bf_prim_off[b], np = h->bf_prim_off[b + 1] - k0;
+            int type = kShellGeneric, ncol = 1;
+            if (all_lmn(b, 0)) {
+                type = kShellS;
+            } else if (b + 2 < h->nbf && all_lmn(b, LX) && all_lmn(b + 1, LY) && all_lmn(b + 2, LZ) && same_prims(b, b + 1) && same_prims(b, b + 2) &&
+                       same_norms(b, b + 1) && same_norms(b, b + 2)) {
+                type = kShellP;
+                ncol = 3;
+            } else if (b + 5 < h->nbf && all_lmn(b, 2 * LX) && all_lmn(b + 1, LX + LY) && all_lmn(b + 2, LX + LZ) && all_lmn(b + 3, 2 * LY) &&
+                       all_lmn(b + 4, LY + LZ) && all_lmn(b + 5, 2 * LZ) && same_prims(b, b + 1) && same_prims(b, b + 2) && same_prims(b, b + 3) &&
+                       same_prims(b, b + 4) && same_prims(b, b + 5) && same_norms(b, b + 3) && same_norms(b, b + 5) && same_norms(b + 1, b + 2) &&
+                       same_norms(b + 1, b + 4)) {
+                type = kShellD;
+                ncol = 6;
+            }
+            shells.push_back(PhiShell{type, b, centre, (int)prims.size(), np, ncol, 0, 0});
+            for (int k = 0; k < np; k++) {
+                const double nb_ = type == kShellD ? h->prim_norm[h->bf_prim_off[b + 1] + k] : 0.0;
+                prims.push_back(PhiPrim{h->prim_coeff[k0 + k], h->prim_norm[k0 + k], nb_, slot_of(k0 + k, centre), h->prim_lmn[k0 + k]});
+            }
+            b += ncol;
+        }
+        const int npass = h->nbp / kPhiCols;
+        std::vector<int> pass_rng(2 * (size_t)npass, 0);
+        for (int pass = 0; pass < npass; pass++) {
+            const int c0 = pass * kPhiCols, c1 = c0 + kPhiCols;
+            int first = (int)shells.size(), last = first;
+            for (int si = 0; si < (int)shells.size(); si++)
+                if (shells[si].col < c1 && shells[si].col + shells[si].ncol > c0) {
+                    first = std::min(first, si);
+                    last = si + 1;
+                }
+            if (first > last) first = last;
+            pass_rng[2 * pass] = first;
+            pass_rng[2 * pass + 1] = last;
+        }
+        h->d_shells.alloc(shells.size());
+        CK(cudaMemcpyAsync(h->d_shells.p, shells.data(), shells.size() * sizeof(PhiShell), cudaMemcpyHostToDevice, st));
         h->d_prims.alloc(prims.size());
         CK(cudaMemcpyAsync(h->d_prims.p, prims.data(), prims.size() * sizeof(PhiPrim), cudaMemcpyHostToDevice, st));
-        PhiBasis B{h->nbf, h->nbp, h->d_bf_center.p, h->d_bf_prim_off.p, h->d_center_exp_off.p, h->d_exp_alpha.p, h->d_prims.p, h->d_center_xyz.p};
+        h->d_pass_rng.upload(pass_rng, st);
+        PhiBasis B{h->nbf, h->nbp, (int)shells.size(), h->d_shells.p, h->d_prims.p, h->d_center_exp_off.p, h->d_exp_alpha.p, h->d_center_xyz.p,
+                   h->d_pass_rng.p};
         const size_t smem = ((size_t)kPhiPts * (kPhiCols + 1) + (size_t)kPhiMaxExp * kPhiPts) * sizeof(double);
         k_phi<<<(unsigned)((g.nloc + kPhiPts - 1) / kPhiPts), kPhiPts, smem, st>>>(g.nloc, B, h->d_x.p, h->d_y.p, h->d_z.p, h->d_phi.p);
         h->launches++;

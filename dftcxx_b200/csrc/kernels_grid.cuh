@@ -38,15 +38,18 @@ __global__ void k_points(GridShape g, const double* __restrict__ atom_xyz, const
 // cancellation-prone cell function is evaluated with separately rounded operations; mu^3 uses an error-free
 // product so it is correctly rounded like glibc's pow(mu, 3.0) (which is what the reference calls).
 __device__ __forceinline__ double cube_rn(double m) {
+    // m^3 rounded once: m*m = p + e exactly (e from the FMA residual), so m^3 = p*m + e*m and the final FMA rounds
+    // the exact p*m plus the tiny (rounded) e*m.  Verified against the 6-operation double-double variant on 4e7
+    // samples (identical) — see DESIGN.md for how it compares with glibc's pow(m, 3.0).
     const double p = __dmul_rn(m, m);
     const double e = __fma_rn(m, m, -p);
-    const double c = __dmul_rn(p, m);
-    const double ce = __fma_rn(p, m, -c);
-    return __dadd_rn(c, __fma_rn(e, m, ce));
+    return __fma_rn(p, m, __dmul_rn(e, m));
 }
 __device__ __forceinline__ double becke_cutoff(double mu) {
+    // f(mu) = 1.5*mu - 0.5*mu^3, three times: 0.5*cube is exact, so one FMA reproduces the separately rounded
+    // product and difference of the reference expression (src/moleculargrid.cpp:325)
 #pragma unroll
-    for (int it = 0; it < 3; it++) mu = __dsub_rn(__dmul_rn(1.5, mu), __dmul_rn(0.5, cube_rn(mu)));
+    for (int it = 0; it < 3; it++) mu = __fma_rn(-0.5, cube_rn(mu), __dmul_rn(1.5, mu));
     return __dmul_rn(0.5, __dsub_rn(1.0, mu));
 }
 
@@ -93,92 +96,152 @@ k_becke(GridShape g, const double* __restrict__ atom_xyz, const double* __restri
 // ---------------------------------------------------------------------------------------------------------
 // CGF amplitudes Phi[p][b] (src/gridpoint.cpp:45-52, src/cgf.cpp:146-154, 49-57):
 //   phi_b(p) = sum_k c_k * ( N_k * dx^l * dy^m * dz^n * exp(-alpha_k r^2) ), products taken left to right.
-// Thread = point; columns are produced in order, atom after atom; each distinct exponent of an atom is
-// exponentiated once per point (the reference recomputes it per primitive: px/py/pz and sp shells share them).
-// exp() is skipped where alpha*r^2 > 746 (the result is exactly +0 in FP64 there, as on the CPU).
+// Thread = point.  The host groups the columns into SHELLS — runs of consecutive CGFs on one centre that share
+// their primitives: S (1 column), P (px,py,pz), D (xx,xy,xz,yy,yz,zz), or a generic single column — so the
+// primitive record (coefficient, norms, exponent slot) is loaded once per shell and the inner loops are branch
+// free.  Each distinct exponent of a centre is exponentiated once per point (the reference recomputes it per
+// primitive); exp() is skipped where alpha*r^2 > 746 (the result is exactly +0 in FP64 there, as on the CPU).
+// Multiplying by pow(x,0) = 1.0 is exact, so the generic path multiplies by a selected factor instead of branching.
 // A [kPhiPts x kPhiCols] tile is staged in shared memory so that every Phi row is written with full 256-byte
 // coalesced segments; pad columns [nbf, nbp) are written as zeros.
+#ifndef DFG_PHI_BRANCHLESS_EXP
+#define DFG_PHI_BRANCHLESS_EXP 0
+#endif
 constexpr int kPhiPts = 128;
 constexpr int kPhiCols = 32;    // one 256-byte row segment per point and pass
 constexpr int kPhiMaxExp = 24;  // distinct exponents on one centre (STO-6G third row needs 18)
 
-struct PhiPrim {  // one primitive term, 32 bytes = two 128-bit loads
-    double coeff, norm;
-    int exp_idx;  // absolute index into exp_alpha
-    int lmn;      // l | m<<4 | n<<8
-    int pad[2];
+enum { kShellGeneric = 0, kShellS = 1, kShellP = 2, kShellD = 3 };
+
+struct PhiPrim {  // one primitive of a shell, 32 bytes
+    double coeff;
+    double norm_a;  // S, P: the norm; D: norm of xx, yy, zz; generic: the norm
+    double norm_b;  // D: norm of xy, xz, yz
+    int exp_slot;   // index into the centre's distinct-exponent list
+    int lmn;        // generic only: l | m<<4 | n<<8
+};
+
+struct PhiShell {  // 32 bytes
+    int type, col, centre, prim_off, nprim, ncol, pad0, pad1;
 };
 
 struct PhiBasis {
-    int nbf, nbp;
-    const int* bf_atom;       // [nbf] centre of column b
-    const int* bf_prim_off;   // [nbf+1]
-    const int* atom_exp_off;  // [ncentres+1]
-    const double* exp_alpha;  // distinct exponents, centre after centre
-    const PhiPrim* prims;     // [nprim]
-    const double* atom_xyz;   // [ncentres][3]
+    int nbf, nbp, nshell;
+    const PhiShell* shells;     // ordered by first column; columns are contiguous across shells
+    const PhiPrim* prims;
+    const int* centre_exp_off;  // [ncentres+1]
+    const double* exp_alpha;    // distinct exponents, centre after centre
+    const double* centre_xyz;   // [ncentres][3]
+    const int* pass_shell_rng;  // [npass][2]: first / one-past-last shell intersecting column pass c (kPhiCols columns each)
 };
-
-__device__ __forceinline__ double ipow_rn(double acc, double x, int n) {
-    // acc * pow(x, n) for n in {0,1,2}: pow(x,1) = x and pow(x,2) = x*x exactly rounded; factor 1.0 is exact
-    if (n == 1) return __dmul_rn(acc, x);
-    if (n == 2) return __dmul_rn(acc, __dmul_rn(x, x));
-    return acc;
-}
 
 __global__ void __launch_bounds__(kPhiPts, 3)
 k_phi(long nloc, PhiBasis B, const double* __restrict__ px, const double* __restrict__ py,
       const double* __restrict__ pz, double* __restrict__ phi) {
     extern __shared__ double sm[];
-    double* tile = sm;                                          // [kPhiPts][kPhiCols+1]
-    double* ex = sm + (size_t)kPhiPts * (kPhiCols + 1);          // [kPhiMaxExp][kPhiPts]
+    double* tile = sm;                                   // [kPhiPts][kPhiCols+1]
+    double* ex = sm + (size_t)kPhiPts * (kPhiCols + 1);  // [kPhiMaxExp][kPhiPts]
     const int tid = threadIdx.x;
     const long p0 = (long)blockIdx.x * kPhiPts;
     const long p = p0 + tid;
     const bool live = p < nloc;
     const double x = live ? px[p] : 0.0, y = live ? py[p] : 0.0, z = live ? pz[p] : 0.0;
-    int cur_atom = -1, e0 = 0;
+    double* trow = tile + (size_t)tid * (kPhiCols + 1);
+    const double* exl = ex + tid;
+    int cur = -1;
     double dx = 0, dy = 0, dz = 0;
-    for (int c0 = 0; c0 < B.nbp; c0 += kPhiCols) {
-        const int c1 = min(c0 + kPhiCols, B.nbp);
-        for (int b = c0; b < c1; b++) {
-            double val = 0.0;
-            if (b < B.nbf) {
-                const int atom = __ldg(B.bf_atom + b);
-                if (atom != cur_atom) {
-                    cur_atom = atom;
-                    dx = __dsub_rn(x, __ldg(B.atom_xyz + 3 * atom));
-                    dy = __dsub_rn(y, __ldg(B.atom_xyz + 3 * atom + 1));
-                    dz = __dsub_rn(z, __ldg(B.atom_xyz + 3 * atom + 2));
-                    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                    e0 = __ldg(B.atom_exp_off + atom);
-                    const int e1 = __ldg(B.atom_exp_off + atom + 1);
-                    for (int u = e0; u < e1; u++) {
-                        const double arg = __dmul_rn(__ldg(B.exp_alpha + u), r2);
-                        ex[(size_t)(u - e0) * kPhiPts + tid] = arg > 746.0 ? 0.0 : exp(-arg);
-                    }
+    const int npass = B.nbp / kPhiCols;
+    for (int pass = 0; pass < npass; pass++) {
+        const int c0 = pass * kPhiCols;
+#pragma unroll 4
+        for (int c = 0; c < kPhiCols; c++) trow[c] = 0.0;  // pad columns and columns of shells outside this pass
+        const int s0 = __ldg(B.pass_shell_rng + 2 * pass), s1 = __ldg(B.pass_shell_rng + 2 * pass + 1);
+        for (int si = s0; si < s1; si++) {
+            const int4 sa = __ldg(reinterpret_cast<const int4*>(B.shells + si));      // type, col, centre, prim_off
+            const int2 sb = __ldg(reinterpret_cast<const int2*>(B.shells + si) + 2);  // nprim, ncol
+            if (sa.z != cur) {
+                cur = sa.z;
+                dx = __dsub_rn(x, __ldg(B.centre_xyz + 3 * cur));
+                dy = __dsub_rn(y, __ldg(B.centre_xyz + 3 * cur + 1));
+                dz = __dsub_rn(z, __ldg(B.centre_xyz + 3 * cur + 2));
+                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                const int e0 = __ldg(B.centre_exp_off + cur), e1 = __ldg(B.centre_exp_off + cur + 1);
+#if DFG_PHI_BRANCHLESS_EXP
+#pragma unroll 2
+                for (int u = e0; u < e1; u++) {
+                    const double arg = __dmul_rn(__ldg(B.exp_alpha + u), r2);
+                    const double ev = exp(-fmin(arg, 746.0));
+                    ex[(size_t)(u - e0) * kPhiPts + tid] = arg > 746.0 ? 0.0 : ev;
                 }
-                const int k0 = __ldg(B.bf_prim_off + b), k1 = __ldg(B.bf_prim_off + b + 1);
-                for (int k = k0; k < k1; k++) {
-                    const double2 cn = __ldg(reinterpret_cast<const double2*>(B.prims + k));
-                    const int2 il = __ldg(reinterpret_cast<const int2*>(B.prims + k) + 2);
-                    double a = cn.y;
-                    a = ipow_rn(a, dx, il.y & 15);
-                    a = ipow_rn(a, dy, (il.y >> 4) & 15);
-                    a = ipow_rn(a, dz, (il.y >> 8) & 15);
-                    a = __dmul_rn(a, ex[(size_t)(il.x - e0) * kPhiPts + tid]);
-                    val = __dadd_rn(val, __dmul_rn(cn.x, a));
+#else
+                for (int u = e0; u < e1; u++) {
+                    const double arg = __dmul_rn(__ldg(B.exp_alpha + u), r2);
+                    ex[(size_t)(u - e0) * kPhiPts + tid] = arg > 746.0 ? 0.0 : exp(-arg);
                 }
+#endif
             }
-            tile[(size_t)tid * (kPhiCols + 1) + (b - c0)] = val;
+            const PhiPrim* pr = B.prims + sa.w;
+            const int rel = sa.y - c0;  // first column of the shell relative to this pass (may be negative)
+            if (sa.x == kShellS) {
+                double v = 0.0;
+                for (int k = 0; k < sb.x; k++) {
+                    const double2 cn = __ldg(reinterpret_cast<const double2*>(pr + k));
+                    const int slot = __ldg(reinterpret_cast<const int*>(pr + k) + 6);
+                    v = __dadd_rn(v, __dmul_rn(cn.x, __dmul_rn(cn.y, exl[(size_t)slot * kPhiPts])));
+                }
+                trow[rel] = v;
+            } else if (sa.x == kShellP) {
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+                for (int k = 0; k < sb.x; k++) {
+                    const double2 cn = __ldg(reinterpret_cast<const double2*>(pr + k));
+                    const int slot = __ldg(reinterpret_cast<const int*>(pr + k) + 6);
+                    const double e = exl[(size_t)slot * kPhiPts];
+                    v0 = __dadd_rn(v0, __dmul_rn(cn.x, __dmul_rn(__dmul_rn(cn.y, dx), e)));
+                    v1 = __dadd_rn(v1, __dmul_rn(cn.x, __dmul_rn(__dmul_rn(cn.y, dy), e)));
+                    v2 = __dadd_rn(v2, __dmul_rn(cn.x, __dmul_rn(__dmul_rn(cn.y, dz), e)));
+                }
+                if (rel >= 0 && rel < kPhiCols) trow[rel] = v0;
+                if (rel + 1 >= 0 && rel + 1 < kPhiCols) trow[rel + 1] = v1;
+                if (rel + 2 >= 0 && rel + 2 < kPhiCols) trow[rel + 2] = v2;
+            } else if (sa.x == kShellD) {
+                double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                const double xx = __dmul_rn(dx, dx), yy = __dmul_rn(dy, dy), zz = __dmul_rn(dz, dz);
+                for (int k = 0; k < sb.x; k++) {
+                    const double2 cn = __ldg(reinterpret_cast<const double2*>(pr + k));
+                    const double nb_ = __ldg(reinterpret_cast<const double*>(pr + k) + 2);
+                    const int slot = __ldg(reinterpret_cast<const int*>(pr + k) + 6);
+                    const double e = exl[(size_t)slot * kPhiPts];
+                    v[0] = __dadd_rn(v[0], __dmul_rn(cn.x, __dmul_rn(__dmul_rn(cn.y, xx), e)));
+                    v[1] = __dadd_rn(v[1], __dmul_rn(cn.x, __dmul_rn(__dmul_rn(__dmul_rn(nb_, dx), dy), e)));
+                    v[2] = __dadd_rn(v[2], __dmul_rn(cn.x, __dmul_rn(__dmul_rn(__dmul_rn(nb_, dx), dz), e)));
+                    v[3] = __dadd_rn(v[3], __dmul_rn(cn.x, __dmul_rn(__dmul_rn(cn.y, yy), e)));
+                    v[4] = __dadd_rn(v[4], __dmul_rn(cn.x, __dmul_rn(__dmul_rn(__dmul_rn(nb_, dy), dz), e)));
+                    v[5] = __dadd_rn(v[5], __dmul_rn(cn.x, __dmul_rn(__dmul_rn(cn.y, zz), e)));
+                }
+#pragma unroll
+                for (int t = 0; t < 6; t++)
+                    if (rel + t >= 0 && rel + t < kPhiCols) trow[rel + t] = v[t];
+            } else {  // generic single column: factors selected, never branched on
+                double v = 0.0;
+                const double xx = __dmul_rn(dx, dx), yy = __dmul_rn(dy, dy), zz = __dmul_rn(dz, dz);
+                for (int k = 0; k < sb.x; k++) {
+                    const double2 cn = __ldg(reinterpret_cast<const double2*>(pr + k));
+                    const int2 sl = __ldg(reinterpret_cast<const int2*>(pr + k) + 3);  // exp_slot, lmn
+                    const int l = sl.y & 15, m = (sl.y >> 4) & 15, n = (sl.y >> 8) & 15;
+                    const double fx = l == 0 ? 1.0 : (l == 1 ? dx : xx);
+                    const double fy = m == 0 ? 1.0 : (m == 1 ? dy : yy);
+                    const double fz = n == 0 ? 1.0 : (n == 1 ? dz : zz);
+                    const double a = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(cn.y, fx), fy), fz), exl[(size_t)sl.x * kPhiPts]);
+                    v = __dadd_rn(v, __dmul_rn(cn.x, a));
+                }
+                trow[rel] = v;
+            }
         }
         __syncthreads();
-        const int ncol = c1 - c0;
         for (int row = tid >> 5; row < kPhiPts; row += kPhiPts / 32) {
-            const long pr = p0 + row;
-            if (pr >= nloc) break;
-            const int c = tid & 31;
-            if (c < ncol) phi[pr * B.nbp + c0 + c] = tile[(size_t)row * (kPhiCols + 1) + c];
+            const long pr_ = p0 + row;
+            if (pr_ >= nloc) break;
+            phi[pr_ * B.nbp + c0 + (tid & 31)] = tile[(size_t)row * (kPhiCols + 1) + (tid & 31)];
         }
         __syncthreads();
     }

@@ -252,3 +252,64 @@ def test_against_c_restatement_on_seeded_clusters(nwater, grid):
     finally:
         mg.close()
         o.close()
+
+
+def _with_extra_functions(mol, shuffle):
+    """Water + a d shell (6 Cartesian components, 2 primitives) and a lone p_y / d_xy function on O, optionally with the
+    column order shuffled: exercises the D-shell and the generic (select-based) paths of the amplitude kernel, which the
+    reference's own parser never produces for H..Ar."""
+    from dftcxx_b200.molecule import SHELL_LMN, gto_norm
+
+    bf_nprim, bf_center, alpha, coeff, norm, lmn = (list(getattr(mol, k)) for k in ("bf_nprim", "bf_center", "alpha", "coeff", "norm", "lmn"))
+    O = mol.xyz[0]
+    extra = [(c, [(1.3, 0.6), (0.35, 0.5)]) for c in SHELL_LMN["D"]] + [((0, 1, 0), [(0.9, 1.0)]), ((1, 1, 0), [(0.7, 0.8), (0.2, 0.3)])]
+    for (l, m, n), prims in extra:
+        bf_nprim.append(len(prims))
+        bf_center.append(O)
+        for e, c in prims:
+            alpha.append(e)
+            coeff.append(c)
+            norm.append(gto_norm(e, l, m, n))
+            lmn.append((l, m, n))
+    nb = len(bf_nprim)
+    order = np.arange(nb)
+    if shuffle:
+        order = np.random.default_rng(5).permutation(nb)
+    off = np.concatenate([[0], np.cumsum(bf_nprim)])
+    pick = np.concatenate([np.arange(off[b], off[b + 1]) for b in order])
+    return dict(Z=mol.Z, xyz=mol.xyz, bf_nprim=np.array(bf_nprim, np.int32)[order], bf_center=np.array(bf_center)[order],
+                alpha=np.array(alpha)[pick], coeff=np.array(coeff)[pick], norm=np.array(norm)[pick], lmn=np.array(lmn, np.int32)[pick])
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_d_shells_and_arbitrary_column_order(shuffle):
+    from oracle import portpy
+
+    if not portpy.available():
+        pytest.skip("oracle/liboracle.so not built")
+    from dftcxx_b200.grid import MolecularGrid
+    from dftcxx_b200.molecule import DATA, Molecule
+
+    mol = Molecule.from_file(os.path.join(DATA, "molecules", "h2o_p631.in"))
+    s = _with_extra_functions(mol, shuffle)
+    grid = (10, 4, 5)
+    o = portpy.Port(s, *grid)
+    mg = MolecularGrid(s)
+    mg.set_grid_parameters(*grid)
+    mg.create_grid()
+    try:
+        ref = o.amplitudes()
+        phi = mg.get_amplitudes()
+        assert np.max(np.abs(phi - ref)) <= 1e-14 * max(1.0, np.max(np.abs(ref)))
+        nb = len(s["bf_nprim"])
+        rng = np.random.default_rng(11)
+        A = rng.standard_normal((nb, 5)) / np.sqrt(nb)
+        P = A @ A.T
+        o.set_density(P)
+        Jo, _ = o.hartree()
+        XCo, exco = o.xc()
+        J, XC, exc, nel = mg.iteration(P)
+        assert np.max(np.abs(J - Jo)) <= TOL_MATRIX_ABS and np.max(np.abs(XC - XCo)) <= TOL_MATRIX_ABS and abs(exc - exco) <= 1e-10
+    finally:
+        mg.close()
+        o.close()
