@@ -321,12 +321,17 @@ void do_build(dftgrid* h) {
         std::vector<int> cost(nitems);
         long W = 0;
         for (int it = 0; it < nitems; it++) {
-            const int tj = pairs[2 * (it % h->npairs) + 1];
-            const char* nc = std::getenv("DFTGRID_NARROW_COST");  // cost of a 64-wide edge tile relative to 10 for a full one
-            cost[it] = std::min(kTileN, h->nbp - tj * kTileN) <= 64 ? (nc ? std::atoi(nc) : 6) : 10;
+            const int ti = pairs[2 * (it % h->npairs)], tj = pairs[2 * (it % h->npairs) + 1];
+            // relative DMMA cost of one k-chunk of this tile pair (full off-diagonal 128x128 tile = 20): a 64-wide
+            // edge tile issues half the DMMAs but pays the same loads (measured ~0.6), a diagonal tile issues 24/32 (8/32 on the edge)
+            const char* nc = std::getenv("DFTGRID_NARROW_COST");
+            const char* dc = std::getenv("DFTGRID_DIAG_COST");
+            const bool narrow = std::min(kTileN, h->nbp - tj * kTileN) <= 64;
+            const int c_narrow = nc ? std::atoi(nc) : 12, c_diag = dc ? std::atoi(dc) : 16;
+            cost[it] = ti == tj ? (narrow ? 8 : c_diag) : (narrow ? c_narrow : 20);
             W += (long)cost[it] * nchunk;
         }
-        const int G = (int)std::max<long>(1, std::min<long>(nsm, W / 20 > 0 ? W / 20 : 1));
+        const int G = (int)std::max<long>(1, std::min<long>(nsm, W / 40 > 0 ? W / 40 : 1));
         std::vector<ConSeg> segs;
         std::vector<int> cta_off(1, 0), item_off(nitems + 1, 0);
         int item = 0;

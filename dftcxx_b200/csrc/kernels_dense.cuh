@@ -232,25 +232,78 @@ __device__ __forceinline__ void con_load_stage(double* st, const double* __restr
     }
 }
 
-template <int NT>
-__device__ __forceinline__ void con_mma_stage(const double* st, bool diag, double (&acc)[4][8][2], int wm, int wn, int lane) {
+// Warp tiling of the 128 x (128|64) output tile: 8 warps stacked along M, each owning MT = 2 row tiles (16 rows) and
+// the whole width (NT = 16 column tiles, 8 for an edge tile).  Per k4-step a warp then scales only 2 A fragments by the
+// point weight (the DMULs compete with DMMA for the FP64 pipe) and issues 32 DMMAs from 2 + 16 fragment loads.
+template <int MT, int NT>
+__device__ __forceinline__ void con_mma_stage(const double* st, bool diag, double (&acc)[32][2], int warp, int lane) {
     const double* As = st;
     const double* Bs = diag ? st : st + kTileK * kLdN;
     const double* ds = st + 2 * kTileK * kLdN;
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int kk = 0; kk < kTileK; kk += 4) {
-        double a[4], b[NT];
+        double a[MT], b[NT];
         const double dv = ds[kk + q];
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++) a[mt] = As[(kk + q) * kLdN + wm * 32 + mt * 8 + g] * dv;
+        for (int mt = 0; mt < MT; mt++) a[mt] = As[(kk + q) * kLdN + warp * (MT * 8) + mt * 8 + g] * dv;
 #pragma unroll
-        for (int nt = 0; nt < NT; nt++) b[nt] = Bs[(kk + q) * kLdN + wn * (NT * 8) + nt * 8 + g];
+        for (int nt = 0; nt < NT; nt++) b[nt] = Bs[(kk + q) * kLdN + nt * 8 + g];
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++)
+        for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt * NT + nt][0], acc[mt * NT + nt][1], a[mt], b[nt]);
     }
+}
+
+// Diagonal tile pair (ti == tj): of the four 64x64 quadrants only (0,0), (0,1) and (1,1) are needed.  Warp w owns row
+// tile w of the upper half (against all 16 column tiles) and row tile 8+w of the lower half (against column tiles
+// 8..15): 24 instead of 32 DMMAs per k4-step with a fully static register layout.  For a 64-wide edge tile (NT = 8)
+// only the upper-left quadrant exists.  The skipped quadrant stays zero; k_contract_reduce never reads it.
+template <int NT>
+__device__ __forceinline__ void con_mma_stage_diag(const double* st, double (&acc)[32][2], int warp, int lane) {
+    const double* As = st;
+    const double* ds = st + 2 * kTileK * kLdN;
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < kTileK; kk += 4) {
+        double b[NT];
+        const double dv = ds[kk + q];
+        const double a0 = As[(kk + q) * kLdN + warp * 8 + g] * dv;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) b[nt] = As[(kk + q) * kLdN + nt * 8 + g];
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) dmma884(acc[nt][0], acc[nt][1], a0, b[nt]);
+        if (NT == 16) {
+            const double a1 = As[(kk + q) * kLdN + 64 + warp * 8 + g] * dv;
+#pragma unroll
+            for (int nt = 8; nt < NT; nt++) dmma884(acc[8 + nt][0], acc[8 + nt][1], a1, b[nt]);
+        }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void con_store_diag(double* out, const double (&acc)[32][2], int warp, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+        *reinterpret_cast<double2*>(out + (warp * 8 + g) * kTileN + nt * 8 + q * 2) = make_double2(acc[nt][0], acc[nt][1]);
+    if (NT == 16) {
+#pragma unroll
+        for (int nt = 8; nt < NT; nt++)
+            *reinterpret_cast<double2*>(out + (64 + warp * 8 + g) * kTileN + nt * 8 + q * 2) = make_double2(acc[8 + nt][0], acc[8 + nt][1]);
+    }
+}
+
+template <int MT, int NT>
+__device__ __forceinline__ void con_store(double* out, const double (&acc)[32][2], int warp, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+            *reinterpret_cast<double2*>(out + (warp * (MT * 8) + mt * 8 + g) * kTileN + nt * 8 + q * 2) =
+                make_double2(acc[mt * NT + nt][0], acc[mt * NT + nt][1]);
 }
 
 // Work decomposition ("stream-K"): the (matrix z, tile pair) items, each nchunk k-chunks long and weighted by their
@@ -269,8 +322,6 @@ k_contract(const double* __restrict__ phi, const double* __restrict__ d0, const 
            double* __restrict__ partial, long nloc, int nbp) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wm = warp & 3, wn = warp >> 2;
-    const int g = lane >> 2, q = lane & 3;
     const int s_begin = cta_seg_off[blockIdx.x], s_end = cta_seg_off[blockIdx.x + 1];
     for (int sidx = s_begin; sidx < s_end; sidx++) {
         const ConSeg sg = segs[sidx];
@@ -282,11 +333,9 @@ k_contract(const double* __restrict__ phi, const double* __restrict__ d0, const 
         const int total = sg.c_end - sg.c_begin;
         const bool narrow = min(kTileN, nbp - cj) <= 64;
 
-        double acc[4][8][2];
+        double acc[32][2];
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-            for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        for (int t = 0; t < 32; t++) acc[t][0] = acc[t][1] = 0.0;
 
         for (int s = 0; s < kStages - 1; s++) {
             if (s < total) con_load_stage(sm + (size_t)s * kConStageDoubles, phi, d, (c_begin + s) * kTileK, nloc, nbp, ci, cj, diag);
@@ -302,25 +351,30 @@ k_contract(const double* __restrict__ phi, const double* __restrict__ d0, const 
                 cp_async_commit();
             }
             const double* st = sm + (size_t)(it % kStages) * kConStageDoubles;
-            if (narrow)
-                con_mma_stage<4>(st, diag, acc, wm, wn, lane);
-            else
-                con_mma_stage<8>(st, diag, acc, wm, wn, lane);
+            if (diag) {
+                if (narrow)
+                    con_mma_stage_diag<8>(st, acc, warp, lane);
+                else
+                    con_mma_stage_diag<16>(st, acc, warp, lane);
+            } else if (narrow) {
+                con_mma_stage<2, 8>(st, false, acc, warp, lane);
+            } else {
+                con_mma_stage<2, 16>(st, false, acc, warp, lane);
+            }
         }
         cp_async_wait<0>();
         __syncthreads();  // every warp is done with the stage buffers before the next segment refills them
         double* out = partial + (size_t)sidx * (size_t)(kTileM * kTileN);
-        const int ntn = narrow ? 4 : 8;
-#pragma unroll
-        for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-            for (int nt = 0; nt < 8; nt++) {
-                const int r = wm * 32 + mt * 8 + g;
-                if (nt < ntn) {
-                    const int c = wn * (ntn * 8) + nt * 8 + q * 2;
-                    *reinterpret_cast<double2*>(out + r * kTileN + c) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-                }
-            }
+        if (diag) {
+            if (narrow)
+                con_store_diag<8>(out, acc, warp, lane);
+            else
+                con_store_diag<16>(out, acc, warp, lane);
+        } else if (narrow) {
+            con_store<2, 8>(out, acc, warp, lane);
+        } else {
+            con_store<2, 16>(out, acc, warp, lane);
+        }
     }
 }
 

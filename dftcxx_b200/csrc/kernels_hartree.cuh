@@ -159,6 +159,16 @@ __global__ void k_poisson(GridShape g, int n /*N+2*/, const double* __restrict__
 // Not-a-knot cubic splines through (r ascending, U_lm) for every (atom, lm): Cspline::generate_spline
 // (src/cspline.cpp:66-142) with the x-only part of the tridiagonal sweep precomputed on the host.
 // Output table coef[atom][interval][lm][4] (a,b,c,d); interval N-1 is the clamp y.back() (src/cspline.cpp:159-161).
+// Position of (l, m) inside one (atom, interval) block of the coefficient table: the +m and -m records sit next to
+// each other (64 contiguous bytes), because the interpolation kernel always needs them together.
+//   slot(l, 0) = l^2,  slot(l, +m) = l^2 + 2m - 1,  slot(l, -m) = l^2 + 2m
+__host__ __device__ __forceinline__ int coef_slot_lm(int l, int m) { return l * l + (m == 0 ? 0 : (m > 0 ? 2 * m - 1 : -2 * m)); }
+__host__ __device__ __forceinline__ int coef_slot(int lm) {
+    int l = 0;
+    while ((l + 1) * (l + 1) <= lm) l++;
+    return coef_slot_lm(l, lm - l * l - l);
+}
+
 struct SplineDev {
     const double* x;    // [N]
     const double* A;    // [N]
@@ -177,6 +187,7 @@ __global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_
     const int lm = (int)(t % g.nlm), atom = (int)(t / g.nlm);
     const int N = g.nrad;
     auto y = [&](int i) -> double { return U_lm[((long)atom * N + (N - 1 - i)) * g.nlm + lm]; };  // ascending r
+    const int slot = coef_slot(lm);
     double* Y = work + t;                        // stride nsys
     double* D = work + (size_t)N * nsys + t;     // stride nsys
     // right-hand sides (src/cspline.cpp:81-109)
@@ -206,9 +217,9 @@ __global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_
         c.y = Di;
         c.z = dx * (3 * dy - 2 * Di - Dn);
         c.w = dx * dx * (-2 * dy + Di + Dn);
-        *reinterpret_cast<double4*>(coef + (((size_t)atom * N + i) * g.nlm + lm) * 4) = c;
+        *reinterpret_cast<double4*>(coef + (((size_t)atom * N + i) * g.nlm + slot) * 4) = c;
     }
-    *reinterpret_cast<double4*>(coef + (((size_t)atom * N + (N - 1)) * g.nlm + lm) * 4) = make_double4(y(N - 1), 0.0, 0.0, 0.0);
+    *reinterpret_cast<double4*>(coef + (((size_t)atom * N + (N - 1)) * g.nlm + slot) * 4) = make_double4(y(N - 1), 0.0, 0.0, 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -328,14 +339,14 @@ k_interp(GridShape g, const double* __restrict__ atom_xyz, const double* __restr
                 pl2 = pl1;
                 pl1 = pl;
                 const double pf = presh[l * (L + 1) + m] * rinv;
-                const int lmp = l * l + l + m;
+                const int lmp = coef_slot_lm(l, m);
                 {
                     const double4 c = *reinterpret_cast<const double4*>(cf + (size_t)lmp * 4);
                     const double sv = c.x + c.y * tt + c.z * tt * tt + c.w * tt * tt * tt;
                     sum += pf * (pl * cm) * sv;
                 }
                 if (m > 0) {
-                    const double4 c = *reinterpret_cast<const double4*>(cf + (size_t)(lmp - 2 * m) * 4);
+                    const double4 c = *reinterpret_cast<const double4*>(cf + (size_t)(lmp + 1) * 4);
                     const double sv = c.x + c.y * tt + c.z * tt * tt + c.w * tt * tt * tt;
                     sum += pf * (pl * sn) * sv;
                 }
@@ -430,12 +441,12 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
                 pl1 = pl;
                 const double pf = presh[l * (L + 1) + m] * rinv;
                 {
-                    const double4 c = cf[l * l + l + m];
+                    const double4 c = cf[l * l + (m == 0 ? 0 : 2 * m - 1)];
                     const double sv = c.x + c.y * tt + c.z * tt2 + c.w * tt3;
                     sum += pf * (pl * cm) * sv;
                 }
                 if (m > 0) {
-                    const double4 c = cf[l * l + l - m];
+                    const double4 c = cf[l * l + 2 * m];
                     const double sv = c.x + c.y * tt + c.z * tt2 + c.w * tt3;
                     sum += pf * (pl * sn) * sv;
                 }
