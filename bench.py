@@ -160,7 +160,7 @@ def reference_fit(workload, mol, prm, threads):
     return float(full), desc, {"a_ms": a, "b_ms": b, "sample_ms": ts}
 
 
-def run_reference(args, mol, prm):
+def run_reference(args, mol, prm, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -169,7 +169,7 @@ def run_reference(args, mol, prm):
     threads = os.cpu_count() or 1
     kind = "reference" if refpy.available() else "unavailable"
     if kind == "unavailable":
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (reference sources absent at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref was not built (reference sources absent at build time)"})
         return
     vals = []
     desc = ""
@@ -182,7 +182,7 @@ def run_reference(args, mol, prm):
            "config": workload_config(args.workload, mol, prm),
            "cpu_baseline": {"value": v, "unit": "ms", "cores": threads, "kind": "reference", "sample": desc},
            "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def workload_config(name, mol, prm):
@@ -206,9 +206,19 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    # Libraries (NCCL, torch) print banners on stdout; the contract is ONE JSON line there.  Everything written to fd 1
+    # while the benchmark runs is diverted to stderr and the JSON line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     mol, prm = load_workload(args.workload)
     if args.impl == "reference":
-        return run_reference(args, mol, prm)
+        return run_reference(args, mol, prm, emit)
 
     import torch
 
@@ -336,7 +346,7 @@ def main():
                 out["cpu_baseline"] = {"value": ms, "unit": "ms", "cores": os.cpu_count() or 1, "kind": "reference", "sample": desc}
             except Exception as e:  # the oracle is a checker, never a dependency of the measured path
                 out["cpu_baseline"] = {"value": None, "unit": "ms", "cores": os.cpu_count() or 1, "kind": "unavailable", "sample": str(e)[:200]}
-        print(json.dumps(out))
+        emit(out)
     g.close()
     if dist:
         dist.destroy_process_group()

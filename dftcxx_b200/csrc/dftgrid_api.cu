@@ -101,7 +101,8 @@ struct dftgrid {
     DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
     DevBuf<int> d_pairs, d_cta_off, d_item_off;
     DevBuf<ConSeg> d_segs;
-    int npairs = 0, nsplit = 1, con_ctas = 1;
+    int npairs = 0, nsplit = 1, con_ctas = 1, interp_chunks = 1;
+    DevBuf<double> d_Vpart;
 
     // pinned staging
     double* h_P = nullptr;
@@ -132,7 +133,11 @@ namespace {
 
 void allreduce(dftgrid* h, double* buf, size_t count) {
     if (h->nranks == 1) return;
-    if (!h->comm) throw std::runtime_error("nranks > 1 but dftgrid_comm_init was not called");
+    if (!h->comm) {
+        // developer switch: time one shard's kernels on a single GPU (results are then partial sums, not the molecule's)
+        if (std::getenv("DFTGRID_DEBUG_SKIP_COMM")) return;
+        throw std::runtime_error("nranks > 1 but dftgrid_comm_init was not called");
+    }
     int rc = nccl_api().AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
     if (rc != 0) throw std::runtime_error(std::string("ncclAllReduce failed: ") + nccl_api().GetErrorString(rc));
 }
@@ -379,6 +384,13 @@ void do_build(dftgrid* h) {
         CK(cudaStreamSynchronize(st));  // the host vectors above go out of scope
     }
 
+    {
+        // source-atom chunks of the interpolation kernel: enough CTAs for >= ~8 full waves (6 CTAs of 128 threads per SM)
+        const long ctas = (g.nloc + 127) / 128, wave = 6L * nsm;
+        long chunks = ctas > 0 ? (8 * wave + ctas - 1) / ctas : 1;
+        h->interp_chunks = (int)std::max<long>(1, std::min<long>(chunks, std::min<long>(g.natoms, 32)));
+        h->d_Vpart.alloc((size_t)h->interp_chunks * (nl + 64));
+    }
     if (!h->h_P) CK(cudaMallocHost(&h->h_P, sizeof(double) * std::max<size_t>(1, (size_t)h->nbf * h->nbf)));
     if (!h->h_res) CK(cudaMallocHost(&h->h_res, sizeof(double) * ((size_t)2 * h->nbf * h->nbf + 2)));
 
@@ -553,24 +565,19 @@ void run_potential(dftgrid* h) {
     record(h, 10);
     if (g.nloc > 0) {
         const size_t smem = ((size_t)g.nrad + (size_t)(g.lmax + 1) * (g.lmax + 1) + 2 * g.lmax + 2) * sizeof(double);
-        const unsigned blocks = (unsigned)((g.nloc + 127) / 128);
-#define DFG_INTERP_ARGS g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p, h->d_Vown.p, h->d_xs.p, h->d_pre.p, h->d_coef.p, h->d_V.p, h->d_dJ.p
-        const char* var = std::getenv("DFTGRID_INTERP_VARIANT");
-        const int variant = var ? std::atoi(var) : 0;
+        const unsigned bx = (unsigned)((g.nloc + 127) / 128);
+        const dim3 blocks(bx, h->interp_chunks);
+#define DFG_INTERP_ARGS g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p, h->d_Vown.p, h->d_xs.p, h->d_pre.p, h->d_coef.p, h->d_Vpart.p
         switch (g.lmax) {  // unrolled kernels for the reference's grid presets (src/settings.cpp:158-187), generic otherwise
             case 5: k_interp_t<5, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
             case 8: k_interp_t<8, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
-            case 10:
-                if (variant == 1) k_interp_t<10, 4><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS);
-                else if (variant == 2) k_interp_t<10, 3><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS);
-                else if (variant == 3) k_interp_t<10, 8><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS);
-                else k_interp_t<10, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS);
-                break;
+            case 10: k_interp_t<10, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
             case 11: k_interp_t<11, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
             default: k_interp<<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
         }
 #undef DFG_INTERP_ARGS
-        h->launches++;
+        k_finish_potential<<<(unsigned)((g.nloc + 255) / 256), 256, 0, st>>>(g.nloc, h->interp_chunks, h->d_Vpart.p, h->d_w.p, h->d_V.p, h->d_dJ.p);
+        h->launches += 2;
     }
     record(h, 11);
     h->have_potential = true;

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(128)
 k_interp(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ px, const double* __restrict__ py,
          const double* __restrict__ pz, const double* __restrict__ w, const double* __restrict__ Vown,
          const double* __restrict__ xs /*[N] ascending*/, const double* __restrict__ pre /*[(lmax+1)^2]*/,
-         const double* __restrict__ coef, double* __restrict__ V, double* __restrict__ dJ) {
+         const double* __restrict__ coef, double* __restrict__ Vpart /*[gridDim.y][nloc]*/) {
     extern __shared__ double sm[];
     const int N = g.nrad, L = g.lmax;
     double* xsh = sm;            // [N]
@@ -273,7 +273,8 @@ k_interp(GridShape g, const double* __restrict__ atom_xyz, const double* __restr
     const int own = (int)((g.shell0 + p / g.nang) / g.nrad);
     const double x = px[p], y = py[p], z = pz[p];
     double Vacc = 0.0;
-    for (int k = 0; k < g.natoms; k++) {
+    const int k_begin = (int)((long)g.natoms * blockIdx.y / gridDim.y), k_end = (int)((long)g.natoms * (blockIdx.y + 1) / gridDim.y);
+    for (int k = k_begin; k < k_end; k++) {
         if (k == own) {
             Vacc += Vown[p];
             continue;
@@ -354,8 +355,7 @@ k_interp(GridShape g, const double* __restrict__ atom_xyz, const double* __restr
         }
         Vacc += sum;
     }
-    V[p] = Vacc;
-    dJ[p] = w[p] * Vacc;
+    Vpart[(size_t)blockIdx.y * g.nloc + p] = Vacc;
 }
 
 // Fully unrolled variant for a compile-time lmax (the presets use 5, 8, 10, 11): all (l, m) loop indices, recurrence
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(128, MINB)
 k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ px, const double* __restrict__ py,
            const double* __restrict__ pz, const double* __restrict__ w, const double* __restrict__ Vown,
            const double* __restrict__ xs, const double* __restrict__ pre, const double* __restrict__ coef,
-           double* __restrict__ V, double* __restrict__ dJ) {
+           double* __restrict__ Vpart /*[gridDim.y][nloc]*/) {
     extern __shared__ double sm[];
     const int N = g.nrad;
     constexpr int NLM = (L + 1) * (L + 1);
@@ -380,7 +380,10 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
     const int own = (int)((g.shell0 + p / g.nang) / g.nrad);
     const double x = px[p], y = py[p], z = pz[p];
     double Vacc = 0.0;
-    for (int k = 0; k < g.natoms; k++) {
+    // blockIdx.y selects a contiguous chunk of source atoms: short CTAs keep the tail wave small when a rank holds
+    // only a fraction of the points; the chunk sums are added in chunk order by k_finish_potential
+    const int k_begin = (int)((long)g.natoms * blockIdx.y / gridDim.y), k_end = (int)((long)g.natoms * (blockIdx.y + 1) / gridDim.y);
+    for (int k = k_begin; k < k_end; k++) {
         if (k == own) {
             Vacc += Vown[p];
             continue;
@@ -454,8 +457,18 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
         }
         Vacc += sum;
     }
-    V[p] = Vacc;
-    dJ[p] = w[p] * Vacc;
+    Vpart[(size_t)blockIdx.y * g.nloc + p] = Vacc;
+}
+
+// V = sum of the atom-chunk partial potentials in chunk order; dJ = w * V feeds the J contraction
+__global__ void k_finish_potential(long nloc, int nchunk, const double* __restrict__ Vpart, const double* __restrict__ w,
+                                   double* __restrict__ V, double* __restrict__ dJ) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nloc) return;
+    double v = 0.0;
+    for (int c = 0; c < nchunk; c++) v += Vpart[(size_t)c * nloc + p];
+    V[p] = v;
+    dJ[p] = w[p] * v;
 }
 
 }  // namespace dfg

@@ -127,7 +127,7 @@ class MolecularGrid:
         self.close()
         self.h = h
         try:
-            if self.nranks > 1:
+            if self.nranks > 1 and comm_id is not False:  # comm_id=False: developer profiling of one shard without NCCL
                 if comm_id is None:
                     raise GridError("nranks > 1 needs the NCCL unique id from rank 0")
                 self._ck(lib().dftgrid_comm_init(self.h, comm_id))

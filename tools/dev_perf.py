@@ -8,8 +8,12 @@ from dftcxx_b200.systems import WORKLOADS, synthetic_density
 def main(name, iters=3):
     fac, (nr, lo, lm) = WORKLOADS[name]
     mol = fac()
-    g = MolecularGrid(mol); g.set_grid_parameters(nr, lo, lm)
-    t = time.time(); g.create_grid(); t1 = time.time() - t
+    rank, nranks = int(os.environ.get("FAKE_RANK", "0")), int(os.environ.get("FAKE_NRANKS", "1"))
+    g = MolecularGrid(mol, rank=rank, nranks=nranks); g.set_grid_parameters(nr, lo, lm)
+    if nranks > 1:
+        os.environ["DFTGRID_DEBUG_SKIP_COMM"] = "1"  # time one shard's kernels on a single GPU (results are partial sums)
+    t = time.time(); g.create_grid(comm_id=False if nranks > 1 else None)
+    t1 = time.time() - t
     tm = g.timings()
     print(name, "natoms", mol.natoms, "nbf", mol.nbf, "npts", g.npoints, "create_grid wall %.3fs" % t1,
           {k: round(tm[k], 3) for k in ("points", "becke", "phi")})
