@@ -564,7 +564,8 @@ void run_potential(dftgrid* h) {
     }
     record(h, 10);
     if (g.nloc > 0) {
-        const size_t smem = ((size_t)g.nrad + (size_t)(g.lmax + 1) * (g.lmax + 1) + 2 * g.lmax + 2) * sizeof(double);
+        const size_t smem_g = ((size_t)g.nrad + (size_t)(g.lmax + 1) * (g.lmax + 1) + 2 * g.lmax + 2) * sizeof(double);
+        const size_t smem = smem_g + (size_t)4 * 2 * g.nlm * 4 * sizeof(double);  // + per-warp staging rows of the unrolled kernels
         const unsigned bx = (unsigned)((g.nloc + 127) / 128);
         const dim3 blocks(bx, h->interp_chunks);
 #define DFG_INTERP_ARGS g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p, h->d_Vown.p, h->d_xs.p, h->d_pre.p, h->d_coef.p, h->d_Vpart.p
@@ -573,7 +574,7 @@ void run_potential(dftgrid* h) {
             case 8: k_interp_t<8, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
             case 10: k_interp_t<10, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
             case 11: k_interp_t<11, 6><<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
-            default: k_interp<<<blocks, 128, smem, st>>>(DFG_INTERP_ARGS); break;
+            default: k_interp<<<blocks, 128, smem_g, st>>>(DFG_INTERP_ARGS); break;
         }
 #undef DFG_INTERP_ARGS
         k_finish_potential<<<(unsigned)((g.nloc + 255) / 256), 256, 0, st>>>(g.nloc, h->interp_chunks, h->d_Vpart.p, h->d_w.p, h->d_V.p, h->d_dJ.p);

@@ -367,27 +367,31 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
            const double* __restrict__ pz, const double* __restrict__ w, const double* __restrict__ Vown,
            const double* __restrict__ xs, const double* __restrict__ pre, const double* __restrict__ coef,
            double* __restrict__ Vpart /*[gridDim.y][nloc]*/) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(32) double sm[];
     const int N = g.nrad;
     constexpr int NLM = (L + 1) * (L + 1);
-    double* xsh = sm;        // [N]
-    double* presh = sm + N;  // [(L+1)^2]
+    // Spline-record staging: the 32 points of a warp usually fall into one or two adjacent radial intervals of a source
+    // atom, so the warp copies those one or two (atom, interval) rows (NLM records of 32 bytes, contiguous) into shared
+    // memory once and every lane then reads its records as broadcast LDS instead of 2*NLM divergent global loads.
+    // Warps spanning more than two intervals fall back to per-lane global loads through the same (generic) pointer.
+    double4* rows = reinterpret_cast<double4*>(sm) + (size_t)(threadIdx.x >> 5) * 2 * NLM;  // [4 warps][2][NLM]
+    double* xsh = sm + (size_t)4 * 2 * NLM * 4;                                              // [N]
+    double* presh = xsh + N;                                                                  // [(L+1)^2]
     for (int i = threadIdx.x; i < N; i += blockDim.x) xsh[i] = xs[i];
     for (int i = threadIdx.x; i < (L + 1) * (L + 1); i += blockDim.x) presh[i] = pre[i];
     __syncthreads();
-    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= g.nloc) return;
+    const int lane = threadIdx.x & 31;
+    const long pr = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = pr < g.nloc;
+    const long p = live ? pr : g.nloc - 1;  // idle lanes of the last warp shadow the last point (never stored)
     const int own = (int)((g.shell0 + p / g.nang) / g.nrad);
     const double x = px[p], y = py[p], z = pz[p];
+    const double vown = Vown[p];
     double Vacc = 0.0;
     // blockIdx.y selects a contiguous chunk of source atoms: short CTAs keep the tail wave small when a rank holds
     // only a fraction of the points; the chunk sums are added in chunk order by k_finish_potential
     const int k_begin = (int)((long)g.natoms * blockIdx.y / gridDim.y), k_end = (int)((long)g.natoms * (blockIdx.y + 1) / gridDim.y);
     for (int k = k_begin; k < k_end; k++) {
-        if (k == own) {
-            Vacc += Vown[p];
-            continue;
-        }
         const double dx = x - atom_xyz[3 * k], dy = y - atom_xyz[3 * k + 1], dz = z - atom_xyz[3 * k + 2];
         const double r = sqrt(dx * dx + dy * dy + dz * dz);
         const double rinv = 1.0 / r;
@@ -411,7 +415,19 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
             iv = hi_ - 1;
             tt = r - xsh[iv];
         }
-        const double4* cf = reinterpret_cast<const double4*>(coef + ((size_t)k * N + iv) * NLM * 4);
+        const double4* grow = reinterpret_cast<const double4*>(coef + ((size_t)k * N) * NLM * 4);  // atom k, interval 0
+        const int iv_min = __reduce_min_sync(0xffffffffu, iv), iv_max = __reduce_max_sync(0xffffffffu, iv);
+        const double4* cf;
+        __syncwarp();  // the previous atom's rows are no longer being read
+        if (iv_max - iv_min <= 1) {
+            const int nrec = (iv_max - iv_min + 1) * NLM;  // the two rows are contiguous in the table
+            const double4* src = grow + (size_t)iv_min * NLM;
+            for (int i = lane; i < nrec; i += 32) rows[i] = src[i];
+            __syncwarp();
+            cf = rows + (iv - iv_min) * NLM;
+        } else {
+            cf = grow + (size_t)iv * NLM;
+        }
         const double tt2 = tt * tt, tt3 = tt2 * tt;
         const double ct = dz / r;
         const double st = sqrt(1.0 - ct * ct);
@@ -421,7 +437,8 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
             c1 = dx / rxy;
             s1 = dy / rxy;
         }
-        double cm = 1.0, sn = 0.0, pmm = 1.0, sum = 0.0;
+        double cm = 1.0, sn = 0.0, pmm = 1.0;
+        double acc4[4] = {0.0, 0.0, 0.0, 0.0};  // independent partial sums: no single serial FMA chain
 #pragma unroll
         for (int m = 0; m <= L; m++) {
             if (m > 0) {
@@ -446,18 +463,19 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
                 {
                     const double4 c = cf[l * l + (m == 0 ? 0 : 2 * m - 1)];
                     const double sv = c.x + c.y * tt + c.z * tt2 + c.w * tt3;
-                    sum += pf * (pl * cm) * sv;
+                    acc4[(l & 1) * 2] += pf * (pl * cm) * sv;
                 }
                 if (m > 0) {
                     const double4 c = cf[l * l + 2 * m];
                     const double sv = c.x + c.y * tt + c.z * tt2 + c.w * tt3;
-                    sum += pf * (pl * sn) * sv;
+                    acc4[(l & 1) * 2 + 1] += pf * (pl * sn) * sv;
                 }
             }
         }
-        Vacc += sum;
+        const double sum = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+        Vacc += k == own ? vown : sum;  // own cell: the tabulated V_fuzzy instead of the interpolated expansion
     }
-    Vpart[(size_t)blockIdx.y * g.nloc + p] = Vacc;
+    if (live) Vpart[(size_t)blockIdx.y * g.nloc + p] = Vacc;
 }
 
 // V = sum of the atom-chunk partial potentials in chunk order; dJ = w * V feeds the J contraction

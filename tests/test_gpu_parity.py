@@ -313,3 +313,37 @@ def test_d_shells_and_arbitrary_column_order(shuffle):
     finally:
         mg.close()
         o.close()
+
+
+@pytest.mark.parametrize("grid", [(8, 2, 3), (12, 5, 6), (25, 9, 9)])
+def test_non_preset_grid_parameters_use_generic_kernels(grid):
+    """radial_points / lebedev_order / lmax overrides (src/settings.cpp:134-150) that match no preset: exercises the
+    generic interpolation kernel (the unrolled ones cover lmax 5, 8, 10, 11) and odd Lebedev orders."""
+    from oracle import portpy
+
+    if not portpy.available():
+        pytest.skip("oracle/liboracle.so not built")
+    from dftcxx_b200.grid import MolecularGrid
+    from dftcxx_b200.molecule import DATA, Molecule
+    from dftcxx_b200.systems import synthetic_density
+
+    mol = Molecule.from_file(os.path.join(DATA, "molecules", "ch4_p631_fine.in"))
+    s = {k: getattr(mol, k) for k in ("Z", "xyz", "bf_nprim", "bf_center", "alpha", "coeff", "norm", "lmn")}
+    o = portpy.Port(s, *grid)
+    mg = MolecularGrid(mol)
+    mg.set_grid_parameters(*grid)
+    mg.create_grid()
+    try:
+        P = synthetic_density(mol)
+        o.set_density(P)
+        Jo, hi = o.hartree()
+        XCo, exco = o.xc()
+        J, XC, exc, nel = mg.iteration(P)
+        xyz, w, wb = o.grid()
+        assert np.array_equal(mg.get_positions(), xyz)
+        assert relerr(mg.get_becke_weights(), wb, BECKE_FLOOR) <= TOL_REL
+        assert np.max(np.abs(mg.get_potential() - hi["V"])) <= 1e-11 * np.max(np.abs(hi["V"]))
+        assert np.max(np.abs(J - Jo)) <= TOL_MATRIX_ABS and np.max(np.abs(XC - XCo)) <= TOL_MATRIX_ABS and abs(exc - exco) <= 1e-10
+    finally:
+        mg.close()
+        o.close()
