@@ -25,7 +25,7 @@ from oracle.refpy import Ref  # noqa: E402
 #            name                   stride  scf iterations (0 = grid only)
 CASES = [("h2o_sto3g", 1, 14), ("h2o_p631", 3, 17), ("he_sto3g", 1, 6), ("co_sto3g_coarse", 1, 8),
          ("h2_sto3g_ultrafine", 7, 6), ("ch4_p631_fine", 11, 16), ("ethane_p631_fine", 17, 6),
-         ("benzene_p631_fine", 37, 4), ("ch4_p631_dense422", 997, 0)]
+         ("benzene_p631_fine", 37, 4), ("ch4_p631_dense422", 997, 0), ("h2o8_p631_fine", 211, 5)]
 
 
 class _M:

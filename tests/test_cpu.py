@@ -13,7 +13,7 @@ from dftcxx_b200 import molecule as M
 from dftcxx_b200 import systems
 
 CASES = ["h2o_sto3g", "h2o_p631", "he_sto3g", "co_sto3g_coarse", "h2_sto3g_ultrafine", "ch4_p631_fine",
-         "ethane_p631_fine", "benzene_p631_fine", "ch4_p631_dense422"]
+         "ethane_p631_fine", "benzene_p631_fine", "ch4_p631_dense422", "h2o8_p631_fine"]
 
 
 # ---------------------------------------------------------------------------------------------- C ABI surface
@@ -183,7 +183,7 @@ def _hostlib():
 
 
 @pytest.mark.parametrize("name", ["h2o_sto3g", "h2o_p631", "he_sto3g", "co_sto3g_coarse", "h2_sto3g_ultrafine", "ch4_p631_fine",
-                                  "ethane_p631_fine", "benzene_p631_fine"])
+                                  "ethane_p631_fine", "benzene_p631_fine", "h2o8_p631_fine"])
 def test_host_one_electron_integrals_match_reference(name):
     """The host's McMurchie-Davidson S and H = T + V against the reference's own matrices (golden scf_S / scf_H):
     an independent algorithm, so agreement also pins the truncated-pi prefactor and the Boys-argument clamp."""

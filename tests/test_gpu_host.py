@@ -16,7 +16,7 @@ from dftcxx_b200 import molecule as M
 pytestmark = pytest.mark.gpu
 
 CASES = ["h2o_sto3g", "h2o_p631", "he_sto3g", "co_sto3g_coarse", "h2_sto3g_ultrafine", "ch4_p631_fine", "ethane_p631_fine",
-         "benzene_p631_fine"]
+         "benzene_p631_fine", "h2o8_p631_fine"]
 
 
 def hostlib():

@@ -13,7 +13,7 @@ from common import BECKE_FLOOR, TOL_MATRIX_ABS, TOL_REL, grid_params, load_golde
 pytestmark = pytest.mark.gpu
 
 CASES = ["h2o_sto3g", "h2o_p631", "he_sto3g", "co_sto3g_coarse", "h2_sto3g_ultrafine", "ch4_p631_fine",
-         "ethane_p631_fine", "benzene_p631_fine"]
+         "ethane_p631_fine", "benzene_p631_fine", "h2o8_p631_fine"]
 
 
 def make_grid(g, **kw):
