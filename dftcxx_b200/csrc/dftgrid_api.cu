@@ -293,7 +293,9 @@ void do_build(dftgrid* h) {
     h->d_dJ.alloc(nlp);
     h->d_dxc.zero(st);
     h->d_dJ.zero(st);
-    h->d_phi.alloc(nl * h->nbp + 64);
+    // whole 32-row chunks must be readable by the bulk-copy producer: rows past nloc are zero
+    h->d_phi.alloc((nl + kTileK - 1) / kTileK * kTileK * (size_t)h->nbp + 64);
+    h->d_phi.zero(st);
     const size_t nsys = (size_t)g.natoms * g.nlm;
     h->d_P.alloc((size_t)h->nbp * h->nbp);
     h->d_P.zero(st);
@@ -398,6 +400,7 @@ void do_build(dftgrid* h) {
                             (int)(((size_t)kPhiPts * (kPhiCols + 1) + (size_t)kPhiMaxExp * kPhiPts) * sizeof(double))));
     CK(cudaFuncSetAttribute(k_rho, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRhoSmemBytes));
     CK(cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConSmemBytes));
+    CK(cudaFuncSetAttribute(k_contract_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConTmaSmemBytes));
     const size_t becke_smem = (size_t)kBeckeWarps * 2 * g.natoms * sizeof(double);
     if (becke_smem > 200 * 1024) throw std::runtime_error("too many atoms for the Becke kernel's shared-memory layout");
     CK(cudaFuncSetAttribute(k_becke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(becke_smem, 1024)));
@@ -590,8 +593,13 @@ void run_contract(dftgrid* h) {
     const GridShape& g = h->g;
     const size_t nb2 = (size_t)h->nbf * h->nbf;
     record(h, 12);
-    k_contract<<<h->con_ctas, kDenseThreads, kConSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_pairs.p, h->d_segs.p, h->d_cta_off.p,
-                                                                  h->d_partial.p, g.nloc, h->nbp);
+    static const bool use_cp_async = std::getenv("DFTGRID_CONTRACT_CPASYNC") != nullptr;  // developer A/B switch
+    if (use_cp_async)
+        k_contract<<<h->con_ctas, kDenseThreads, kConSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_pairs.p, h->d_segs.p, h->d_cta_off.p,
+                                                                      h->d_partial.p, g.nloc, h->nbp);
+    else
+        k_contract_tma<<<h->con_ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_pairs.p, h->d_segs.p,
+                                                                              h->d_cta_off.p, h->d_partial.p, h->nbp);
     k_contract_reduce<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 0.5,
                                                          h->d_res.p + nb2, h->d_res.p);
     h->launches += 2;

@@ -346,8 +346,10 @@ k_contract(const double* __restrict__ phi, const double* __restrict__ d0, const 
             __syncthreads();
             {
                 const int nx = it + kStages - 1;
+#ifndef DFG_ABLATE_LOADS
                 if (nx < total)
                     con_load_stage(sm + (size_t)(nx % kStages) * kConStageDoubles, phi, d, (c_begin + nx) * kTileK, nloc, nbp, ci, cj, diag);
+#endif
                 cp_async_commit();
             }
             const double* st = sm + (size_t)(it % kStages) * kConStageDoubles;
@@ -364,6 +366,127 @@ k_contract(const double* __restrict__ phi, const double* __restrict__ d0, const 
         }
         cp_async_wait<0>();
         __syncthreads();  // every warp is done with the stage buffers before the next segment refills them
+        double* out = partial + (size_t)sidx * (size_t)(kTileM * kTileN);
+        if (diag) {
+            if (narrow)
+                con_store_diag<8>(out, acc, warp, lane);
+            else
+                con_store_diag<16>(out, acc, warp, lane);
+        } else if (narrow) {
+            con_store<2, 8>(out, acc, warp, lane);
+        } else {
+            con_store<2, 16>(out, acc, warp, lane);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-fed variant of k_contract: a ninth (producer) warp streams the Phi rows of every stage into shared memory with
+// bulk asynchronous copies (cp.async.bulk -> SASS UBLKCP, one 1 KB row per lane) that signal an mbarrier; the eight
+// DMMA warps never touch global memory, wait on the "full" barrier of a stage and release it through an "empty"
+// barrier — no __syncthreads() and no per-thread cp.async / address arithmetic in the tensor loop, and the pipeline
+// keeps running across segment boundaries.  Same arithmetic, same partial-tile layout as k_contract.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kConTmaThreads = kDenseThreads + 32;
+constexpr size_t kConTmaSmemBytes = (size_t)kStages * kConStageDoubles * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
+
+// phi must be readable for whole 32-row chunks (rows past nloc are zero-filled by the host side), d0/d1 likewise.
+__global__ void __launch_bounds__(kConTmaThreads, 1)
+k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, const double* __restrict__ d1,
+               const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs, const int* __restrict__ cta_seg_off,
+               double* __restrict__ partial, int nbp) {
+    extern __shared__ __align__(128) double sm[];
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)kStages * kConStageDoubles);
+    unsigned long long* empty = full + kStages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(full + s, 1);   // the producer's arrive.expect_tx
+            mbar_init(empty + s, 8);  // one arrival per DMMA warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int s_begin = cta_seg_off[blockIdx.x], s_end = cta_seg_off[blockIdx.x + 1];
+    unsigned n = 0;  // running stage counter, continues across segments
+    if (warp == 8) {
+        // ===== producer warp =====
+        for (int sidx = s_begin; sidx < s_end; sidx++) {
+            const ConSeg sg = segs[sidx];
+            const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
+            const int ci = ti * kTileM, cj = tj * kTileN;
+            const bool diag = ti == tj;
+            const double* d = sg.z == 0 ? d0 : d1;
+            const unsigned wi = (unsigned)min(kTileM, nbp - ci) * 8u, wj = (unsigned)min(kTileN, nbp - cj) * 8u;  // valid row bytes
+            const unsigned bytes = kTileK * (wi + (diag ? 0u : wj)) + kTileK * 8u;
+            for (int c = sg.c_begin; c < sg.c_end; c++, n++) {
+                const unsigned stage = n % kStages, round = n / kStages;
+                double* st = sm + (size_t)stage * kConStageDoubles;
+                mbar_wait(empty + stage, (round & 1u) ^ 1u);
+                if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes);
+                __syncwarp();
+                const double* row = phi + ((size_t)c * kTileK + lane) * (size_t)nbp;
+                bulk_copy_g2s(st + lane * kLdN, row + ci, wi, full + stage);
+                if (!diag) bulk_copy_g2s(st + kTileK * kLdN + lane * kLdN, row + cj, wj, full + stage);
+                if (lane == 0) bulk_copy_g2s(st + 2 * kTileK * kLdN, d + (size_t)c * kTileK, kTileK * 8u, full + stage);
+            }
+        }
+        return;
+    }
+    // ===== DMMA warps =====
+    for (int sidx = s_begin; sidx < s_end; sidx++) {
+        const ConSeg sg = segs[sidx];
+        const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
+        const bool diag = ti == tj;
+        const bool narrow = min(kTileN, nbp - tj * kTileN) <= 64;
+        double acc[32][2];
+#pragma unroll
+        for (int t = 0; t < 32; t++) acc[t][0] = acc[t][1] = 0.0;
+        for (int c = sg.c_begin; c < sg.c_end; c++, n++) {
+            const unsigned stage = n % kStages, round = n / kStages;
+            const double* st = sm + (size_t)stage * kConStageDoubles;
+            mbar_wait(full + stage, round & 1u);
+            if (diag) {
+                if (narrow)
+                    con_mma_stage_diag<8>(st, acc, warp, lane);
+                else
+                    con_mma_stage_diag<16>(st, acc, warp, lane);
+            } else if (narrow) {
+                con_mma_stage<2, 8>(st, false, acc, warp, lane);
+            } else {
+                con_mma_stage<2, 16>(st, false, acc, warp, lane);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);
+        }
         double* out = partial + (size_t)sidx * (size_t)(kTileM * kTileN);
         if (diag) {
             if (narrow)
