@@ -293,8 +293,8 @@ void do_build(dftgrid* h) {
     h->d_dJ.alloc(nlp);
     h->d_dxc.zero(st);
     h->d_dJ.zero(st);
-    // whole 32-row chunks must be readable by the bulk-copy producer: rows past nloc are zero
-    h->d_phi.alloc((nl + kTileK - 1) / kTileK * kTileK * (size_t)h->nbp + 64);
+    // whole 128-row tiles / 32-row chunks must be readable by the bulk-copy producers: rows past nloc are zero
+    h->d_phi.alloc((nl + kTileM - 1) / kTileM * kTileM * (size_t)h->nbp + 64);
     h->d_phi.zero(st);
     const size_t nsys = (size_t)g.natoms * g.nlm;
     h->d_P.alloc((size_t)h->nbp * h->nbp);
@@ -334,7 +334,7 @@ void do_build(dftgrid* h) {
             const char* nc = std::getenv("DFTGRID_NARROW_COST");
             const char* dc = std::getenv("DFTGRID_DIAG_COST");
             const bool narrow = std::min(kTileN, h->nbp - tj * kTileN) <= 64;
-            const int c_narrow = nc ? std::atoi(nc) : 12, c_diag = dc ? std::atoi(dc) : 16;
+            const int c_narrow = nc ? std::atoi(nc) : 11, c_diag = dc ? std::atoi(dc) : 15;
             cost[it] = ti == tj ? (narrow ? 8 : c_diag) : (narrow ? c_narrow : 20);
             W += (long)cost[it] * nchunk;
         }
@@ -399,6 +399,7 @@ void do_build(dftgrid* h) {
     CK(cudaFuncSetAttribute(k_phi, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(((size_t)kPhiPts * (kPhiCols + 1) + (size_t)kPhiMaxExp * kPhiPts) * sizeof(double))));
     CK(cudaFuncSetAttribute(k_rho, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRhoSmemBytes));
+    CK(cudaFuncSetAttribute(k_rho_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRhoTmaSmemBytes));
     CK(cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConSmemBytes));
     CK(cudaFuncSetAttribute(k_contract_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConTmaSmemBytes));
     const size_t becke_smem = (size_t)kBeckeWarps * 2 * g.natoms * sizeof(double);
@@ -510,7 +511,11 @@ void run_density(dftgrid* h) {
     const long nshell = (long)g.natoms * g.nrad;
     record(h, 4);
     if (g.nloc > 0) {
-        k_rho<<<(unsigned)((g.nloc + kTileM - 1) / kTileM), kDenseThreads, kRhoSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_rho.p, g.nloc, h->nbp);
+        static const bool rho_cp_async = std::getenv("DFTGRID_RHO_CPASYNC") != nullptr;  // developer A/B switch
+        if (rho_cp_async)
+            k_rho<<<(unsigned)((g.nloc + kTileM - 1) / kTileM), kDenseThreads, kRhoSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_rho.p, g.nloc, h->nbp);
+        else
+            k_rho_tma<<<(unsigned)((g.nloc + kTileM - 1) / kTileM), kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_rho.p, g.nloc, h->nbp);
         h->launches++;
     }
     record(h, 5);

@@ -501,6 +501,127 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA-fed variant of k_rho (same schedule and arithmetic as k_rho): the producer warp copies, per stage, the 128 Phi
+// row pieces (256 B each, four per lane) and the 32 rows of the P block with cp.async.bulk into the padded tiles; the
+// eight DMMA warps synchronise through mbarriers only.  phi must be readable for whole 128-row tiles.
+constexpr int kRhoTmaThreads = kDenseThreads + 32;
+constexpr size_t kRhoTmaSmemBytes = (size_t)kStages * kRhoStageDoubles * sizeof(double) + 2 * kTileM * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
+
+// 9 warps: one SM sub-partition hosts 3 of them, so ptxas caps the kernel at 168 registers per thread
+__global__ void __launch_bounds__(kRhoTmaThreads, 1)
+k_rho_tma(const double* __restrict__ phi, const double* __restrict__ P, double* __restrict__ rho, long nloc, int nbp) {
+    extern __shared__ __align__(128) double sm[];
+    double* red = sm + (size_t)kStages * kRhoStageDoubles;  // [2][128]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(red + 2 * kTileM);
+    unsigned long long* empty = full + kStages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const long p0 = (long)blockIdx.x * kTileM;
+    const int nk = nbp / kTileK;
+    const int nslab = (nbp + kTileN - 1) / kTileN;
+    int total = 0;
+    for (int J = 0; J < nslab; J++) total += nk - J * (kTileN / kTileK);
+
+    if (warp == 8) {
+        // ===== producer warp =====
+        RhoStep ld{0, 0, nbp};
+        for (int it = 0; it < total; it++) {
+            const unsigned stage = (unsigned)it % kStages, round = (unsigned)it / kStages;
+            double* st = sm + (size_t)stage * kRhoStageDoubles;
+            const int slab = ld.slab * kTileN, kc = ld.chunk() * kTileK;
+            const unsigned wb = (unsigned)min(kTileN, nbp - slab) * 8u;
+            mbar_wait(empty + stage, (round & 1u) ^ 1u);
+            if (lane == 0) mbar_arrive_expect_tx(full + stage, kTileM * kTileK * 8u + kTileK * wb);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int row = lane + 32 * r;
+                bulk_copy_g2s(st + row * kLdK, phi + (size_t)(p0 + row) * nbp + kc, kTileK * 8u, full + stage);
+            }
+            bulk_copy_g2s(st + kTileM * kLdK + lane * kLdN, P + (size_t)(kc + lane) * nbp + slab, wb, full + stage);
+            ld.advance();
+        }
+        return;
+    }
+    // ===== DMMA warps =====
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, q = lane & 3;
+    double rowsum[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[4][8][2];
+    RhoStep cs{0, 0, nbp};
+    for (int it = 0; it < total; it++) {
+        const unsigned stage = (unsigned)it % kStages, round = (unsigned)it / kStages;
+        const int slab = cs.slab * kTileN;
+        const int ncols = min(kTileN, nbp - slab);
+        const bool narrow = ncols <= 64;
+        if (cs.i == 0) {
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        }
+        if (cs.i == cs.outer()) {
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {
+                    acc[mt][nt][0] *= 2.0;
+                    acc[mt][nt][1] *= 2.0;
+                }
+        }
+        mbar_wait(full + stage, round & 1u);
+        const double* st = sm + (size_t)stage * kRhoStageDoubles;
+        if (narrow)
+            rho_mma_stage<4>(st, acc, wm, wn, lane);
+        else
+            rho_mma_stage<8>(st, acc, wm, wn, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);
+        if (cs.i == cs.count() - 1) {
+            const int ntn = narrow ? 4 : 8;
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+                const long p = p0 + wm * 32 + mt * 8 + g;
+                if (p < nloc) {
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        if (nt < ntn) {
+                            const int col = slab + wn * (ntn * 8) + nt * 8 + q * 2;
+                            if (col < nbp) {
+                                const double2 f = *reinterpret_cast<const double2*>(phi + p * (long)nbp + col);
+                                rowsum[mt] = fma(acc[mt][nt][0], f.x, rowsum[mt]);
+                                rowsum[mt] = fma(acc[mt][nt][1], f.y, rowsum[mt]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        cs.advance();
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+        double v = rowsum[mt];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (q == 0) red[wn * kTileM + wm * 32 + mt * 8 + g] = v;
+    }
+    // named barrier over the 256 DMMA threads only (the producer warp has already left)
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    if (tid < kTileM) {
+        const long p = p0 + tid;
+        if (p < nloc) rho[p] = 2.0 * (red[tid] + red[kTileM + tid]);
+    }
+}
+
 // out0/out1: nb x nb (symmetric => row/column-major agnostic).  Each thread sums one element over the item's partial
 // tiles [item_slot_off[item], item_slot_off[item+1]) in order.  grid = (npairs, 2).
 __global__ void k_contract_reduce(const double* __restrict__ partial, const int* __restrict__ pair_ij, const int* __restrict__ item_slot_off,
