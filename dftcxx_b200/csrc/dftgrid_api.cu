@@ -103,6 +103,12 @@ struct dftgrid {
     DevBuf<ConSeg> d_segs;
     int npairs = 0, nsplit = 1, con_ctas = 1, interp_chunks = 1;
     DevBuf<double> d_Vpart;
+    // binned interpolation (see kernels_hartree.cuh): pairs sorted by (source atom, spline interval) at build time
+    bool binned = false;
+    int bin_R = 2, bin_nkeys = 0;
+    long bin_nitems = 0;
+    DevBuf<int> d_binoff, d_pair_point, d_slot_of;
+    DevBuf<double> d_pair_out;
 
     // pinned staging
     double* h_P = nullptr;
@@ -205,6 +211,59 @@ float elapsed(dftgrid* h, int a, int b) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]));
     return ms;
+}
+
+// Sort the (local point, source atom) pairs of the cross-atom interpolation into (atom, spline interval) bins.
+// Geometry only, so it is done once per grid.  Falls back to the point-parallel kernels when lmax is not one of the
+// presets, the pair count does not fit 32-bit slots, or the lists do not fit in free device memory.
+void build_pair_bins(dftgrid* h) {
+    const GridShape& g = h->g;
+    cudaStream_t st = h->stream;
+    h->binned = false;
+    if (std::getenv("DFTGRID_INTERP_POINTWISE")) return;  // developer A/B switch
+    if (!(g.lmax == 5 || g.lmax == 8 || g.lmax == 10 || g.lmax == 11)) return;
+    if (g.nloc == 0 || g.natoms < 2) return;
+    if (const char* r = std::getenv("DFTGRID_INTERP_R")) h->bin_R = std::atoi(r);
+    if (h->bin_R < 2 || h->bin_R > 4) h->bin_R = 2;
+    const int unit = 32 * h->bin_R;
+    const int nkeys = g.natoms * g.nrad;
+    const double pairs_max = (double)g.nloc * (g.natoms - 1) + (double)nkeys * unit;
+    if (pairs_max >= 2.0e9) return;
+    size_t mem_free = 0, mem_total = 0;
+    CK(cudaMemGetInfo(&mem_free, &mem_total));
+    if (pairs_max * 12.0 + (double)g.nloc * g.natoms * 4.0 > 0.5 * (double)mem_free) return;
+
+    DevBuf<int> d_counts, d_cursor;
+    d_counts.alloc(nkeys);
+    d_counts.zero(st);
+    const unsigned blocks = (unsigned)((g.nloc + 255) / 256);
+    const size_t smem = (size_t)g.nrad * sizeof(double);
+    k_bin_pairs<<<blocks, 256, smem, st>>>(g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, d_counts.p, nullptr, nullptr, nullptr, nullptr);
+    std::vector<int> counts(nkeys), binoff(nkeys + 1, 0);
+    CK(cudaMemcpyAsync(counts.data(), d_counts.p, nkeys * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    long total = 0;
+    for (int i = 0; i < nkeys; i++) {
+        binoff[i] = (int)total;
+        total += ((long)counts[i] + unit - 1) / unit * unit;
+    }
+    if (total >= 2147483647L) return;
+    binoff[nkeys] = (int)total;
+    h->bin_nkeys = nkeys;
+    h->bin_nitems = total / unit;
+    h->d_binoff.upload(binoff, st);
+    d_cursor.alloc(nkeys);
+    d_cursor.zero(st);
+    h->d_pair_point.alloc((size_t)total + 1);
+    CK(cudaMemsetAsync(h->d_pair_point.p, 0xFF, ((size_t)total + 1) * sizeof(int), st));
+    h->d_slot_of.alloc((size_t)g.natoms * g.nloc);
+    h->d_pair_out.alloc((size_t)total + 1);
+    k_bin_pairs<<<blocks, 256, smem, st>>>(g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, d_counts.p, h->d_binoff.p, d_cursor.p,
+                                           h->d_pair_point.p, h->d_slot_of.p);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));  // binoff (host vector) and the scratch buffers go out of scope
+    h->binned = true;
 }
 
 void do_build(dftgrid* h) {
@@ -496,6 +555,7 @@ void do_build(dftgrid* h) {
         h->launches++;
     }
     record(h, 3);
+    build_pair_bins(h);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     h->t_ms[DFTGRID_T_POINTS] = elapsed(h, 0, 1);
@@ -564,14 +624,41 @@ void run_potential(dftgrid* h) {
     record(h, 9);
     k_poisson<<<(unsigned)((nsys + 63) / 64), 64, 0, st>>>(g, g.nrad + 2, h->d_lu.p, h->d_perm.p, h->d_lo.p, h->d_hi.p, h->d_rtab.p,
                                                           rho_lm, h->d_qatom.p, h->d_work.p, h->d_U_lm.p);
-    k_spline<<<(unsigned)((nsys + 63) / 64), 64, 0, st>>>(g, h->spline, h->d_U_lm.p, h->d_work.p, h->d_coef.p);
+    k_spline<<<(unsigned)((nsys + 63) / 64), 64, 0, st>>>(g, h->spline, h->d_U_lm.p, h->d_pre.p, h->d_work.p, h->d_coef.p);
     h->launches += 2;
     if (g.nloc > 0) {
         k_v_own<<<(unsigned)g.nshell_loc, 128, g.nlm * sizeof(double), st>>>(g, h->d_rtab.p, h->d_leb.p, h->d_Yt.p, h->d_U_lm.p, h->d_Vown.p);
         h->launches++;
     }
     record(h, 10);
-    if (g.nloc > 0) {
+    if (g.nloc > 0 && h->binned) {
+        if (h->bin_nitems > 0) {
+            const unsigned bx = (unsigned)((h->bin_nitems + kBinWarps - 1) / kBinWarps);
+            const size_t smem = (size_t)kBinWarps * g.nlm * 4 * sizeof(double);
+#define DFG_BIN_ARGS g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, h->d_coef.p, h->d_binoff.p, h->bin_nkeys, h->d_pair_point.p, h->bin_nitems, h->d_pair_out.p
+#define DFG_BIN_CASE(LL)                                                                                        \
+    case LL:                                                                                                    \
+        if (h->bin_R == 4)                                                                                      \
+            k_interp_bin<LL, 4><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                               \
+        else if (h->bin_R == 2)                                                                                 \
+            k_interp_bin<LL, 2><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                               \
+        else                                                                                                    \
+            k_interp_bin<LL, 3><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                               \
+        break;
+            switch (g.lmax) {
+                DFG_BIN_CASE(5)
+                DFG_BIN_CASE(8)
+                DFG_BIN_CASE(10)
+                DFG_BIN_CASE(11)
+                default: throw std::runtime_error("binned interpolation: unsupported lmax");
+            }
+#undef DFG_BIN_CASE
+#undef DFG_BIN_ARGS
+            h->launches++;
+        }
+        k_finish_binned<<<(unsigned)((g.nloc + 255) / 256), 256, 0, st>>>(g, h->d_slot_of.p, h->d_pair_out.p, h->d_Vown.p, h->d_w.p, h->d_V.p, h->d_dJ.p);
+        h->launches++;
+    } else if (g.nloc > 0) {
         const size_t smem_g = ((size_t)g.nrad + (size_t)(g.lmax + 1) * (g.lmax + 1) + 2 * g.lmax + 2) * sizeof(double);
         const size_t smem = smem_g + (size_t)4 * 2 * g.nlm * 4 * sizeof(double);  // + per-warp staging rows of the unrolled kernels
         const unsigned bx = (unsigned)((g.nloc + 127) / 128);

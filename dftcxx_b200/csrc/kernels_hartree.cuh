@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "host_tables.h"
+#include <type_traits>
 
 namespace dfg {
 
@@ -179,8 +180,8 @@ struct SplineDev {
     double fw0, fh0, lh1, lw1;
 };
 
-__global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_lm, double* __restrict__ work /*[2][N][nsys]*/,
-                         double* __restrict__ coef) {
+__global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_lm, const double* __restrict__ pre /*[(lmax+1)^2]*/,
+                         double* __restrict__ work /*[2][N][nsys]*/, double* __restrict__ coef) {
     const long nsys = (long)g.natoms * g.nlm;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsys) return;
@@ -188,6 +189,15 @@ __global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_
     const int N = g.nrad;
     auto y = [&](int i) -> double { return U_lm[((long)atom * N + (N - 1 - i)) * g.nlm + lm]; };  // ascending r
     const int slot = coef_slot(lm);
+    // the records carry the real-Y_lm prefactor pre_{l|m|} (src/spherical_harmonics.cpp:28-33), so the interpolation
+    // kernels multiply P_l^|m| {cos|sin} by the record value only
+    double pf;
+    {
+        int l = 0;
+        while ((l + 1) * (l + 1) <= lm) l++;
+        const int m = lm - l * l - l;
+        pf = pre[l * (g.lmax + 1) + (m < 0 ? -m : m)];
+    }
     double* Y = work + t;                        // stride nsys
     double* D = work + (size_t)N * nsys + t;     // stride nsys
     // right-hand sides (src/cspline.cpp:81-109)
@@ -213,13 +223,13 @@ __global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_
         const double dy = (y(i + 1) - y(i)) * dx;
         const double Di = D[(size_t)i * nsys], Dn = D[(size_t)(i + 1) * nsys];
         double4 c;
-        c.x = y(i);
-        c.y = Di;
-        c.z = dx * (3 * dy - 2 * Di - Dn);
-        c.w = dx * dx * (-2 * dy + Di + Dn);
+        c.x = pf * y(i);
+        c.y = pf * Di;
+        c.z = pf * (dx * (3 * dy - 2 * Di - Dn));
+        c.w = pf * (dx * dx * (-2 * dy + Di + Dn));
         *reinterpret_cast<double4*>(coef + (((size_t)atom * N + i) * g.nlm + slot) * 4) = c;
     }
-    *reinterpret_cast<double4*>(coef + (((size_t)atom * N + (N - 1)) * g.nlm + slot) * 4) = make_double4(y(N - 1), 0.0, 0.0, 0.0);
+    *reinterpret_cast<double4*>(coef + (((size_t)atom * N + (N - 1)) * g.nlm + slot) * 4) = make_double4(pf * y(N - 1), 0.0, 0.0, 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -339,7 +349,7 @@ k_interp(GridShape g, const double* __restrict__ atom_xyz, const double* __restr
                     pl = ((double)(2 * l - 1) * ct * pl1 + (double)(-l - m + 1) * pl2) * rj[l - m];
                 pl2 = pl1;
                 pl1 = pl;
-                const double pf = presh[l * (L + 1) + m] * rinv;
+                const double pf = rinv;  // pre_lm is folded into the spline records
                 const int lmp = coef_slot_lm(l, m);
                 {
                     const double4 c = *reinterpret_cast<const double4*>(cf + (size_t)lmp * 4);
@@ -459,7 +469,7 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
                     pl = ((double)(2 * l - 1) * ct * pl1 + (double)(-l - m + 1) * pl2) * (1.0 / (double)(l - m));
                 pl2 = pl1;
                 pl1 = pl;
-                const double pf = presh[l * (L + 1) + m] * rinv;
+                const double pf = rinv;  // pre_lm is folded into the spline records
                 {
                     const double4 c = cf[l * l + (m == 0 ? 0 : 2 * m - 1)];
                     const double sv = c.x + c.y * tt + c.z * tt2 + c.w * tt3;
@@ -485,6 +495,226 @@ __global__ void k_finish_potential(long nloc, int nchunk, const double* __restri
     if (p >= nloc) return;
     double v = 0.0;
     for (int c = 0; c < nchunk; c++) v += Vpart[(size_t)c * nloc + p];
+    V[p] = v;
+    dJ[p] = w[p] * v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Binned cross-atom interpolation.
+//
+// The unrolled kernel above is bound by the register-fill bandwidth of the on-chip load path: every lane needs the
+// 32-byte spline record of each (l,m) term (8 L1/shared wavefronts per warp and term against 4.5 clocks of FP64
+// work).  Which record a (point p, source atom k) pair needs depends only on the geometry: the radial interval
+// ("row") of |p - R_k| on the shared abscissa.  So at grid-build time all pairs are sorted into bins keyed by
+// (k, row); at every SCF iteration one warp evaluates 32*R pairs of ONE bin, each lane holding R points in registers,
+// and every record fetched from the warp's staged copy of the row is used R times.  Per-pair results go to out[slot]
+// and k_finish_binned adds a point's contributions in source-atom order, exactly the order of the reference's loop
+// (src/moleculargrid.cpp:350-377), so the result does not depend on how the bins were filled.
+__device__ __forceinline__ double pair_dist(double dx, double dy, double dz) { return sqrt(dx * dx + dy * dy + dz * dz); }
+
+// Clamped interval lookup of Cspline::eval (src/cspline.cpp:151-172): row N-1 is the y.back() clamp.
+__device__ __forceinline__ int spline_row(double r, const double* xsh, int N) {
+    if (r < xsh[0]) return 0;
+    if (r >= xsh[N - 1]) return N - 1;
+    int lo_ = 0, hi_ = N - 1;  // x[lo_] < r <= x[hi_] (or r == x[0]): first i with r <= x_i
+    while (hi_ - lo_ > 1) {
+        const int mid = (lo_ + hi_) >> 1;
+        if (r <= xsh[mid])
+            hi_ = mid;
+        else
+            lo_ = mid;
+    }
+    return hi_ - 1;
+}
+
+// Pass 1 (cursor == nullptr): counts[k*N + row] += 1 for every local (p, k != own) pair.
+// Pass 2: slot = binoff[key] + position inside the bin; pair_point[slot] = p, slot_of[k][p] = slot (-1 for k == own).
+// Lanes of a warp that hit the same bin are aggregated into one atomic.
+__global__ void __launch_bounds__(256)
+k_bin_pairs(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ px, const double* __restrict__ py,
+            const double* __restrict__ pz, const double* __restrict__ xs, int* __restrict__ counts, const int* __restrict__ binoff,
+            int* __restrict__ cursor, int* __restrict__ pair_point, int* __restrict__ slot_of) {
+    extern __shared__ double xsh[];
+    const int N = g.nrad;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) xsh[i] = xs[i];
+    __syncthreads();
+    const long pr = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = pr < g.nloc;
+    const long p = live ? pr : g.nloc - 1;
+    const int lane = threadIdx.x & 31;
+    const int own = (int)((g.shell0 + p / g.nang) / g.nrad);
+    const double x = px[p], y = py[p], z = pz[p];
+    for (int k = 0; k < g.natoms; k++) {
+        int row = -1;
+        if (live && k != own) row = spline_row(pair_dist(x - atom_xyz[3 * k], y - atom_xyz[3 * k + 1], z - atom_xyz[3 * k + 2]), xsh, N);
+        const unsigned grp = __match_any_sync(0xffffffffu, row);
+        const int leader = __ffs(grp) - 1;
+        const int key = k * N + row;
+        if (cursor == nullptr) {
+            if (row >= 0 && lane == leader) atomicAdd(&counts[key], __popc(grp));
+        } else {
+            int base = 0;
+            if (row >= 0 && lane == leader) base = atomicAdd(&cursor[key], __popc(grp));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (row >= 0) {
+                const int slot = binoff[key] + base + __popc(grp & ((1u << lane) - 1u));
+                pair_point[slot] = (int)p;
+                slot_of[(size_t)k * g.nloc + p] = slot;
+            } else if (live) {
+                slot_of[(size_t)k * g.nloc + p] = -1;
+            }
+        }
+    }
+}
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+constexpr int kBinWarps = 4;  // warps (= work items) per CTA of the binned kernel
+
+// One warp per item = 32*R consecutive slots of one bin (bins are padded to a multiple of 32*R; pad slots hold -1).
+// Arithmetic per pair: Legendre columns by the reference's recurrences (src/spherical_harmonics.cpp:81-117),
+// cos/sin(m phi) by angle addition, cubic in Horner form; 1/r is applied once to the pair's sum.
+template <int L, int R>
+__global__ void __launch_bounds__(kBinWarps * 32, (R >= 4 ? 3 : (R == 3 ? 4 : 5)))
+k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ px, const double* __restrict__ py,
+             const double* __restrict__ pz, const double* __restrict__ xs, const double* __restrict__ coef,
+             const int* __restrict__ binoff, int nkeys, const int* __restrict__ pair_point, long nitems, double* __restrict__ out) {
+    constexpr int NLM = (L + 1) * (L + 1);
+    extern __shared__ __align__(32) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long item = (long)blockIdx.x * kBinWarps + warp;
+    if (item >= nitems) return;
+    double4* rowbuf = reinterpret_cast<double4*>(sm) + (size_t)warp * NLM;
+    const long slot0 = item * (32 * R);
+    int key = 0;
+    {
+        int hi_ = nkeys;  // largest key with binoff[key] <= slot0 (empty bins repeat the offset of the next one)
+        while (hi_ - key > 1) {
+            const int mid = (key + hi_) >> 1;
+            if ((long)binoff[mid] <= slot0)
+                key = mid;
+            else
+                hi_ = mid;
+        }
+    }
+    const int N = g.nrad;
+    const int k = key / N, row = key - k * N;
+    {
+        const double4* src = reinterpret_cast<const double4*>(coef) + (size_t)key * NLM;
+        for (int i = lane; i < NLM; i += 32) rowbuf[i] = src[i];
+    }
+    const double ax = atom_xyz[3 * k], ay = atom_xyz[3 * k + 1], az = atom_xyz[3 * k + 2];
+    const double x_first = xs[0], x_row = xs[row];
+    double tt[R], ct[R], st[R], c1[R], s1[R], rinv[R], cm[R], sn[R], pmm[R], acc[R];
+    bool live[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int p = pair_point[slot0 + j * 32 + lane];
+        live[j] = p >= 0;
+        double dx = 1.0, dy = 1.0, dz = 1.0;  // pad lanes evaluate a harmless dummy
+        if (live[j]) {
+            dx = px[p] - ax;
+            dy = py[p] - ay;
+            dz = pz[p] - az;
+        }
+        const double r = pair_dist(dx, dy, dz);
+        rinv[j] = 1.0 / r;
+        tt[j] = r < x_first ? 0.0 : r - x_row;  // below the first node the spline is clamped to y.front()
+        ct[j] = dz / r;  // cos(theta) = z/r by true division: exactly +-1 on the axis, like cos(acos(z/r))
+        st[j] = sqrt(1.0 - ct[j] * ct[j]);
+        const double rxy = sqrt(dx * dx + dy * dy);
+        c1[j] = 1.0;
+        s1[j] = 0.0;  // atan2(0,0) = 0
+        if (rxy > 0.0) {
+            const double ri = 1.0 / rxy;
+            c1[j] = dx * ri;
+            s1[j] = dy * ri;
+        }
+        cm[j] = 1.0;
+        sn[j] = 0.0;
+        pmm[j] = 1.0;
+        acc[j] = 0.0;
+    }
+    __syncwarp();
+    // compile-time (m, l) loops: every recurrence constant and record offset is an immediate
+    static_for<0, L + 1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        double pl1[R], pl2[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if (m > 0) {
+                pmm[j] *= -(double)(2 * m - 1) * st[j];
+                const double cn = cm[j] * c1[j] - sn[j] * s1[j];
+                sn[j] = sn[j] * c1[j] + cm[j] * s1[j];
+                cm[j] = cn;
+            }
+            pl2[j] = 0.0;
+            pl1[j] = pmm[j];
+        }
+        static_for<m, L + 1>([&](auto lc) {
+            constexpr int l = decltype(lc)::value;
+            const double4 cc = rowbuf[l * l + (m == 0 ? 0 : 2 * m - 1)];
+            double4 cs = make_double4(0.0, 0.0, 0.0, 0.0);
+            if (m > 0) cs = rowbuf[l * l + 2 * m];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                double pl;
+                if (l == m) {
+                    pl = pmm[j];
+                } else if (l == m + 1) {
+                    pl = ct[j] * (double)(2 * m + 1) * pmm[j];
+                } else {  // (l-m) P_l^m = (2l-1) x P_{l-1}^m - (l+m-1) P_{l-2}^m with the constants folded
+                    constexpr double A = (double)(2 * l - 1) / (double)(l - m > 0 ? l - m : 1);
+                    constexpr double B = (double)(-l - m + 1) / (double)(l - m > 0 ? l - m : 1);
+                    pl = fma(A, ct[j] * pl1[j], B * pl2[j]);
+                }
+                pl2[j] = pl1[j];
+                pl1[j] = pl;
+                const double svc = fma(fma(fma(cc.w, tt[j], cc.z), tt[j], cc.y), tt[j], cc.x);
+                if (m > 0) {
+                    const double svs = fma(fma(fma(cs.w, tt[j], cs.z), tt[j], cs.y), tt[j], cs.x);
+                    acc[j] = fma(pl, fma(svs, sn[j], svc * cm[j]), acc[j]);
+                } else {
+                    acc[j] = fma(pl, svc, acc[j]);
+                }
+            }
+        });
+    });
+#pragma unroll
+    for (int j = 0; j < R; j++)
+        if (live[j]) out[slot0 + j * 32 + lane] = acc[j] * rinv[j];
+}
+
+// V(p) = sum over source atoms in ascending order of (own cell: tabulated V_fuzzy | interpolated expansion);
+// dJ = w * V feeds the J contraction.
+__global__ void k_finish_binned(GridShape g, const int* __restrict__ slot_of, const double* __restrict__ out,
+                                const double* __restrict__ Vown, const double* __restrict__ w, double* __restrict__ V,
+                                double* __restrict__ dJ) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.nloc) return;
+    const double vown = Vown[p];
+    double v = 0.0;
+    int k = 0;
+    for (; k + 4 <= g.natoms; k += 4) {
+        int s[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) s[u] = slot_of[(size_t)(k + u) * g.nloc + p];
+        double c[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) c[u] = s[u] < 0 ? vown : out[s[u]];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v += c[u];
+    }
+    for (; k < g.natoms; k++) {
+        const int s = slot_of[(size_t)k * g.nloc + p];
+        v += s < 0 ? vown : out[s];
+    }
     V[p] = v;
     dJ[p] = w[p] * v;
 }
