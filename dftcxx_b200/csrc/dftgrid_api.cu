@@ -107,7 +107,7 @@ struct dftgrid {
     bool binned = false;
     int bin_R = 2, bin_nkeys = 0;
     long bin_nitems = 0;
-    DevBuf<int> d_binoff, d_pair_point, d_slot_of;
+    DevBuf<int> d_binoff, d_item_key, d_pair_point, d_slot_of;
     DevBuf<double> d_pair_out;
 
     // pinned staging
@@ -260,7 +260,10 @@ void build_pair_bins(dftgrid* h) {
     h->d_pair_out.alloc((size_t)total + 1);
     k_bin_pairs<<<blocks, 256, smem, st>>>(g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, d_counts.p, h->d_binoff.p, d_cursor.p,
                                            h->d_pair_point.p, h->d_slot_of.p);
-    h->launches += 2;
+    h->d_item_key.alloc((size_t)h->bin_nitems + 1);
+    if (h->bin_nitems > 0)
+        k_item_keys<<<(unsigned)((h->bin_nitems + 255) / 256), 256, 0, st>>>(h->d_binoff.p, nkeys, unit, h->bin_nitems, h->d_item_key.p);
+    h->launches += 3;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));  // binoff (host vector) and the scratch buffers go out of scope
     h->binned = true;
@@ -635,16 +638,19 @@ void run_potential(dftgrid* h) {
         if (h->bin_nitems > 0) {
             const unsigned bx = (unsigned)((h->bin_nitems + kBinWarps - 1) / kBinWarps);
             const size_t smem = (size_t)kBinWarps * g.nlm * 4 * sizeof(double);
-#define DFG_BIN_ARGS g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, h->d_coef.p, h->d_binoff.p, h->bin_nkeys, h->d_pair_point.p, h->bin_nitems, h->d_pair_out.p
+#define DFG_BIN_ARGS g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, h->d_coef.p, h->d_item_key.p, h->d_pair_point.p, h->bin_nitems, h->d_pair_out.p
 #define DFG_BIN_CASE(LL)                                                                                        \
     case LL:                                                                                                    \
         if (h->bin_R == 4)                                                                                      \
-            k_interp_bin<LL, 4><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                               \
-        else if (h->bin_R == 2)                                                                                 \
-            k_interp_bin<LL, 2><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                               \
+            k_interp_bin<LL, 4, 3><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                            \
+        else if (h->bin_R == 3)                                                                                 \
+            k_interp_bin<LL, 3, 4><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                            \
+        else if (five)                                                                                          \
+            k_interp_bin<LL, 2, 5><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                            \
         else                                                                                                    \
-            k_interp_bin<LL, 3><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                               \
+            k_interp_bin<LL, 2, 6><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                            \
         break;
+            static const bool five = std::getenv("DFTGRID_INTERP_MINB5") != nullptr;  // developer A/B switch
             switch (g.lmax) {
                 DFG_BIN_CASE(5)
                 DFG_BIN_CASE(8)

@@ -567,6 +567,23 @@ k_bin_pairs(GridShape g, const double* __restrict__ atom_xyz, const double* __re
     }
 }
 
+// item_key[item] = bin of the item's 32*R slots: the largest key with binoff[key] <= first slot (empty bins repeat the
+// offset of the next one, so the last of a run of equal offsets is the non-empty bin).
+__global__ void k_item_keys(const int* __restrict__ binoff, int nkeys, int unit, long nitems, int* __restrict__ item_key) {
+    const long item = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= nitems) return;
+    const long slot0 = item * unit;
+    int key = 0, hi_ = nkeys;
+    while (hi_ - key > 1) {
+        const int mid = (key + hi_) >> 1;
+        if ((long)binoff[mid] <= slot0)
+            key = mid;
+        else
+            hi_ = mid;
+    }
+    item_key[item] = key;
+}
+
 template <int I, int N, class F>
 __device__ __forceinline__ void static_for(F&& f) {
     if constexpr (I < N) {
@@ -580,11 +597,11 @@ constexpr int kBinWarps = 4;  // warps (= work items) per CTA of the binned kern
 // One warp per item = 32*R consecutive slots of one bin (bins are padded to a multiple of 32*R; pad slots hold -1).
 // Arithmetic per pair: Legendre columns by the reference's recurrences (src/spherical_harmonics.cpp:81-117),
 // cos/sin(m phi) by angle addition, cubic in Horner form; 1/r is applied once to the pair's sum.
-template <int L, int R>
-__global__ void __launch_bounds__(kBinWarps * 32, (R >= 4 ? 3 : (R == 3 ? 4 : 5)))
+template <int L, int R, int MINB>
+__global__ void __launch_bounds__(kBinWarps * 32, MINB)
 k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ px, const double* __restrict__ py,
              const double* __restrict__ pz, const double* __restrict__ xs, const double* __restrict__ coef,
-             const int* __restrict__ binoff, int nkeys, const int* __restrict__ pair_point, long nitems, double* __restrict__ out) {
+             const int* __restrict__ item_key, const int* __restrict__ pair_point, long nitems, double* __restrict__ out) {
     constexpr int NLM = (L + 1) * (L + 1);
     extern __shared__ __align__(32) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -592,22 +609,22 @@ k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __r
     if (item >= nitems) return;
     double4* rowbuf = reinterpret_cast<double4*>(sm) + (size_t)warp * NLM;
     const long slot0 = item * (32 * R);
-    int key = 0;
-    {
-        int hi_ = nkeys;  // largest key with binoff[key] <= slot0 (empty bins repeat the offset of the next one)
-        while (hi_ - key > 1) {
-            const int mid = (key + hi_) >> 1;
-            if ((long)binoff[mid] <= slot0)
-                key = mid;
-            else
-                hi_ = mid;
-        }
-    }
+    // independent loads first: the item's bin and its R point indices per lane
+    const int key = item_key[item];
+    int pidx[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) pidx[j] = pair_point[slot0 + j * 32 + lane];
     const int N = g.nrad;
     const int k = key / N, row = key - k * N;
     {
-        const double4* src = reinterpret_cast<const double4*>(coef) + (size_t)key * NLM;
-        for (int i = lane; i < NLM; i += 32) rowbuf[i] = src[i];
+        // stage the bin's row of records with asynchronous copies; they land while the lane's geometry is set up
+        const double2* src = reinterpret_cast<const double2*>(coef) + (size_t)key * (2 * NLM);  // 16-byte units
+        double2* dst2 = reinterpret_cast<double2*>(rowbuf);
+        for (int i = lane; i < 2 * NLM; i += 32) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(dst2 + i);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
     const double ax = atom_xyz[3 * k], ay = atom_xyz[3 * k + 1], az = atom_xyz[3 * k + 2];
     const double x_first = xs[0], x_row = xs[row];
@@ -615,7 +632,7 @@ k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __r
     bool live[R];
 #pragma unroll
     for (int j = 0; j < R; j++) {
-        const int p = pair_point[slot0 + j * 32 + lane];
+        const int p = pidx[j];
         live[j] = p >= 0;
         double dx = 1.0, dy = 1.0, dz = 1.0;  // pad lanes evaluate a harmless dummy
         if (live[j]) {
@@ -641,6 +658,7 @@ k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __r
         pmm[j] = 1.0;
         acc[j] = 0.0;
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncwarp();
     // compile-time (m, l) loops: every recurrence constant and record offset is an immediate
     static_for<0, L + 1>([&](auto mc) {
