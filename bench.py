@@ -292,9 +292,13 @@ def main():
     phases = g.timings()
     ms_step = max_over_ranks(dev_ms / args.steps)
 
-    # ---- e2e: host buffers through the C ABI
+    # ---- e2e: host buffers through the C ABI.  P and the result matrices live in pinned host memory (the SCF
+    # driver's own buffers); every step copies P host->device and [J | XC | E_xc | N_el] device->host.
+    P_host = torch.from_numpy(np.ascontiguousarray(P)).pin_memory().numpy()
+    out_host = (torch.empty((mol.nbf, mol.nbf), dtype=torch.float64).pin_memory().numpy(),
+                torch.empty((mol.nbf, mol.nbf), dtype=torch.float64).pin_memory().numpy())
     for _ in range(2):
-        g.iteration(P)
+        g.iteration(P_host, out=out_host)
     g.synchronize()
     barrier()
     t0 = time.perf_counter()
@@ -302,7 +306,7 @@ def main():
         if small:
             flush.zero_()
             torch.cuda.synchronize()
-        J, XC, exc, nel = g.iteration(P)
+        J, XC, exc, nel = g.iteration(P_host, out=out_host)
     g.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     barrier()

@@ -718,14 +718,29 @@ __global__ void k_pad_P(const double* __restrict__ Praw, double* __restrict__ P,
     P[(size_t)i * nbp + j] = Praw[t];
 }
 
-void upload_P(dftgrid* h, const double* P) {
+// True when the caller's host buffer is page-locked (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor):
+// the DMA engine can then read or write it directly and the bounce through the handle's own pinned staging is skipped.
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Returns true when the copy reads the caller's buffer asynchronously (the caller's buffer must stay untouched until
+// the stream has been synchronised).
+bool upload_P(dftgrid* h, const double* P) {
     if (!h->built) throw std::runtime_error("dftgrid_build has not been called");
     const size_t nb2 = (size_t)h->nbf * h->nbf;
-    std::memcpy(h->h_P, P, nb2 * sizeof(double));
-    CK(cudaMemcpyAsync(h->d_Praw.p, h->h_P, nb2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const bool direct = is_pinned_host(P);
+    if (!direct) std::memcpy(h->h_P, P, nb2 * sizeof(double));
+    CK(cudaMemcpyAsync(h->d_Praw.p, direct ? P : h->h_P, nb2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     // P is symmetric, so Eigen's column-major and our row-major padded copy coincide
     k_pad_P<<<(unsigned)((nb2 + 255) / 256), 256, 0, h->stream>>>(h->d_Praw.p, h->d_P.p, h->nbf, h->nbp);
     h->launches++;
+    return direct;
 }
 
 void finish_timings(dftgrid* h) {
@@ -857,7 +872,7 @@ int dftgrid_nlm(const dftgrid_t* h) { return h->g.nlm; }
 int dftgrid_upload_density(dftgrid_t* h, const double* P) {
     return guarded([&] {
         use_device(h);
-        upload_P(h, P);
+        if (upload_P(h, P)) CK(cudaStreamSynchronize(h->stream));  // the caller may reuse P as soon as this returns
     });
 }
 
@@ -928,17 +943,27 @@ int dftgrid_download_results(dftgrid_t* h, double* J, double* XC, double* exc, d
     return guarded([&] {
         use_device(h);
         const size_t nb2 = (size_t)h->nbf * h->nbf;
-        CK(cudaMemcpyAsync(h->h_res, h->d_res.p, (2 * nb2 + 2) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        // page-locked caller buffers receive their matrix straight from the DMA engine; others go through h_res
+        const bool dj = J && is_pinned_host(J), dx = XC && is_pinned_host(XC);
+        if (dj) CK(cudaMemcpyAsync(J, h->d_res.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (J && !dj) CK(cudaMemcpyAsync(h->h_res, h->d_res.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (dx) CK(cudaMemcpyAsync(XC, h->d_res.p + nb2, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (XC && !dx) CK(cudaMemcpyAsync(h->h_res + nb2, h->d_res.p + nb2, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_res + 2 * nb2, h->d_res.p + 2 * nb2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        if (J) std::memcpy(J, h->h_res, nb2 * sizeof(double));
-        if (XC) std::memcpy(XC, h->h_res + nb2, nb2 * sizeof(double));
+        if (J && !dj) std::memcpy(J, h->h_res, nb2 * sizeof(double));
+        if (XC && !dx) std::memcpy(XC, h->h_res + nb2, nb2 * sizeof(double));
         if (exc) *exc = h->h_res[2 * nb2];
         if (nelec) *nelec = h->h_res[2 * nb2 + 1];
     });
 }
 
 int dftgrid_iteration(dftgrid_t* h, const double* P, double* J, double* XC, double* exc, double* nelec) {
-    int rc = dftgrid_upload_density(h, P);
+    // P is consumed by the time the download below has synchronised the stream, so a pinned P is read in place
+    int rc = guarded([&] {
+        use_device(h);
+        upload_P(h, P);
+    });
     if (rc) return rc;
     rc = dftgrid_iteration_device(h);
     if (rc) return rc;

@@ -167,10 +167,18 @@ class MolecularGrid:
         self._ck(lib().dftgrid_electron_count(self.h, C.cast(C.byref(n), _dp)))
         return n.value
 
-    def iteration(self, P):
-        """One SCF iteration's grid work through the single-call entry point -> (J, XC, E_xc, N_el)."""
-        J = np.zeros((self.nbf, self.nbf))
-        XC = np.zeros((self.nbf, self.nbf))
+    def iteration(self, P, out=None):
+        """One SCF iteration's grid work through the single-call entry point -> (J, XC, E_xc, N_el).
+        out = (J, XC): caller-owned result arrays to fill (C-contiguous float64 nbf x nbf, e.g. views of pinned host
+        memory, which the library then DMAs into directly); fresh arrays otherwise."""
+        if out is None:
+            J = np.empty((self.nbf, self.nbf))
+            XC = np.empty((self.nbf, self.nbf))
+        else:
+            J, XC = out
+            for a in (J, XC):
+                if a.dtype != np.float64 or a.shape != (self.nbf, self.nbf) or not a.flags.c_contiguous:
+                    raise ValueError("out arrays must be C-contiguous float64 of shape (nbf, nbf)")
         exc, nel = C.c_double(), C.c_double()
         self._ck(lib().dftgrid_iteration(self.h, _ptr(self._mat(P)), _ptr(J), _ptr(XC), C.cast(C.byref(exc), _dp),
                                          C.cast(C.byref(nel), _dp)))

@@ -347,3 +347,48 @@ def test_non_preset_grid_parameters_use_generic_kernels(grid):
     finally:
         mg.close()
         o.close()
+
+
+def test_pinned_host_buffers_are_used_in_place():
+    """Page-locked caller buffers (the SCF driver's own P / J / XC) are DMA'd directly; same bits as pageable ones."""
+    import torch
+
+    g = load_golden("benzene_p631_fine")
+    mg = make_grid(g)
+    try:
+        nb = g["P"].shape[0]
+        J0, XC0, exc0, nel0 = mg.iteration(g["P"])
+        Pp = torch.from_numpy(np.ascontiguousarray(g["P"])).pin_memory().numpy()
+        out = (torch.empty((nb, nb), dtype=torch.float64).pin_memory().numpy(),
+               torch.empty((nb, nb), dtype=torch.float64).pin_memory().numpy())
+        J1, XC1, exc1, nel1 = mg.iteration(Pp, out=out)
+        assert J1 is out[0] and XC1 is out[1]
+        assert np.array_equal(J0, J1) and np.array_equal(XC0, XC1) and exc0 == exc1 and nel0 == nel1
+        with pytest.raises(ValueError):
+            mg.iteration(g["P"], out=(np.zeros((nb, nb), dtype=np.float32), np.zeros((nb, nb))))
+    finally:
+        mg.close()
+
+
+def test_binned_and_point_parallel_interpolation_agree(monkeypatch):
+    """The cross-atom interpolation has two schedules: pairs binned by (source atom, spline interval) at grid build
+    (default for the preset lmax values) and the point-parallel kernels (fallback).  Same potential either way."""
+    g = load_golden("h2o8_p631_fine")
+    mg = make_grid(g)
+    try:
+        mg.iteration(g["P"])
+        Vb = mg.get_potential()
+        Jb = mg.calculate_hartree_potential()
+    finally:
+        mg.close()
+    monkeypatch.setenv("DFTGRID_INTERP_POINTWISE", "1")
+    mp = make_grid(g)
+    try:
+        mp.iteration(g["P"])
+        Vp = mp.get_potential()
+        Jp = mp.calculate_hartree_potential()
+    finally:
+        mp.close()
+    assert np.max(np.abs(Vb - Vp)) <= 1e-12 * np.max(np.abs(Vp))
+    assert np.max(np.abs(Jb - Jp)) <= 1e-12
+    assert np.max(np.abs(Vb[g["idx"]] - g["V"])) <= 1e-11 * np.max(np.abs(g["V"]))

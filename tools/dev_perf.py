@@ -22,7 +22,7 @@ def main(name, iters=3):
     for it in range(iters):
         t = time.time(); J, XC, exc, nel = g.iteration(P); t1 = time.time() - t
         tm = g.timings()
-        print("  iter %d wall %.2f ms" % (it, t1 * 1e3), {k: round(v, 3) for k, v in tm.items() if k not in ("points", "becke", "phi")}, "nel %.6f exc %.6f" % (nel, exc))
+        print("  iter %d wall %.2f ms" % (it, t1 * 1e3), {k: round(v, 3) for k, v in tm.items() if k not in ("points", "becke", "phi")}, "nel %.6f exc %.6f trJ %.9f" % (nel, exc, float(np.trace(J))))
     F = 2.0 * g.npoints * g.nbf ** 2
     print("  rho: %.2f TFLOP/s (full 2*N*nb^2)   contract: %.2f TFLOP/s (2 sym matrices, N*nb*(nb+1) each)" % (
         F / (tm["rho"] * 1e-3) / 1e12, 2.0 * g.npoints * g.nbf * (g.nbf + 1) / (tm["contract"] * 1e-3) / 1e12))
