@@ -99,7 +99,8 @@ struct dftgrid {
     DevBuf<double> d_x, d_y, d_z, d_w, d_wb, d_rho, d_dxc, d_exw, d_V, d_Vown, d_dJ, d_phi;
     // device: per iteration
     DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
-    DevBuf<int> d_pairs, d_cta_off, d_item_off;
+    DevBuf<int> d_pairs, d_cta_off, d_item_off, d_chunk_ids;
+    long n_active_chunks = 0;
     DevBuf<ConSeg> d_segs;
     int npairs = 0, nsplit = 1, con_ctas = 1, interp_chunks = 1;
     DevBuf<double> d_Vpart;
@@ -211,6 +212,107 @@ float elapsed(dftgrid* h, int a, int b) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]));
     return ms;
+}
+
+// Stream-K schedule of the [XC | J] contraction over `nchunk` (non-zero) 32-point chunks: equal DMMA cost per CTA,
+// one CTA per SM.
+void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
+    cudaStream_t st = h->stream;
+    std::vector<int> pairs;
+    const int nt = (h->nbp + kTileM - 1) / kTileM;
+    for (int i = 0; i < nt; i++)
+        for (int j = i; j < nt; j++) {
+            pairs.push_back(i);
+            pairs.push_back(j);
+        }
+    h->npairs = (int)pairs.size() / 2;
+    h->d_pairs.upload(pairs, st);
+    const int nitems = 2 * h->npairs;
+    std::vector<int> cost(nitems);
+    long W = 0;
+    for (int it = 0; it < nitems; it++) {
+        const int ti = pairs[2 * (it % h->npairs)], tj = pairs[2 * (it % h->npairs) + 1];
+        // relative cost of one k-chunk of this tile pair (full off-diagonal 128x128 tile = 20): a 64-wide edge tile
+        // issues half the DMMAs but pays the same loads (measured ~0.6); a diagonal tile issues 17 of 32 DMMAs per
+        // warp (8 of 32 on the edge)
+        const char* nc = std::getenv("DFTGRID_NARROW_COST");
+        const char* dc = std::getenv("DFTGRID_DIAG_COST");
+        const bool narrow = std::min(kTileN, h->nbp - tj * kTileN) <= 64;
+        const int c_narrow = nc ? std::atoi(nc) : 11, c_diag = dc ? std::atoi(dc) : 12;
+        cost[it] = ti == tj ? (narrow ? 8 : c_diag) : (narrow ? c_narrow : 20);
+        W += (long)cost[it] * nchunk;
+    }
+    const int G = (int)std::max<long>(1, std::min<long>(nsm, W / 40 > 0 ? W / 40 : 1));
+    std::vector<ConSeg> segs;
+    std::vector<int> cta_off(1, 0), item_off(nitems + 1, 0);
+    int item = 0;
+    long cpos = 0;  // next unassigned chunk of `item`
+    long done = 0;  // cost units assigned so far
+    for (int c = 0; c < G; c++) {
+        const long target = W * (c + 1) / G;  // cumulative cost this CTA should reach
+        while (item < nitems && (done < target || c == G - 1)) {
+            long take = (target - done + cost[item] - 1) / cost[item];
+            if (c == G - 1) take = nchunk - cpos;
+            take = std::min(take, nchunk - cpos);
+            if (take > 0) {
+                segs.push_back(ConSeg{item / h->npairs, item % h->npairs, (int)cpos, (int)(cpos + take)});
+                cpos += take;
+                done += take * cost[item];
+            }
+            if (cpos == nchunk) {
+                item++;
+                cpos = 0;
+                item_off[item] = (int)segs.size();
+            } else if (c != G - 1) {
+                break;
+            }
+        }
+        cta_off.push_back((int)segs.size());
+    }
+    for (int it = item + 1; it <= nitems; it++) item_off[it] = (int)segs.size();
+    if (nchunk == 0) {  // empty shard: every item still gets one (empty) segment so that the reduction writes zeros
+        segs.clear();
+        cta_off.assign(1, 0);
+        for (int it = 0; it < nitems; it++) {
+            item_off[it] = it;
+            segs.push_back(ConSeg{it / h->npairs, it % h->npairs, 0, 0});
+        }
+        item_off[nitems] = nitems;
+        cta_off.push_back(nitems);
+    }
+    h->con_ctas = (int)cta_off.size() - 1;
+    h->nsplit = (int)segs.size();
+    h->d_segs.alloc(segs.size());
+    CK(cudaMemcpyAsync(h->d_segs.p, segs.data(), segs.size() * sizeof(ConSeg), cudaMemcpyHostToDevice, st));
+    h->d_cta_off.upload(cta_off, st);
+    h->d_item_off.upload(item_off, st);
+    h->d_partial.alloc((size_t)segs.size() * kTileM * kTileN);
+    CK(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+}
+
+// Lists of the 32-point chunks / 128-point tiles of Phi that hold any non-zero amplitude (k_chunk_flags), and the
+// contraction schedule over the non-zero chunks.
+void build_active_lists(dftgrid* h, int nsm) {
+    const GridShape& g = h->g;
+    cudaStream_t st = h->stream;
+    const long nchunk = (g.nloc + kTileK - 1) / kTileK;
+    std::vector<int> flags((size_t)nchunk, 1);
+    if (nchunk > 0 && !std::getenv("DFTGRID_NO_ZERO_SKIP")) {  // developer A/B switch
+        DevBuf<int> d_flags;
+        d_flags.alloc((size_t)nchunk);
+        k_chunk_flags<<<(unsigned)((nchunk * 32 + 255) / 256), 256, 0, st>>>(h->d_phi.p, nchunk, h->nbp, d_flags.p);
+        h->launches++;
+        CK(cudaMemcpyAsync(flags.data(), d_flags.p, (size_t)nchunk * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    std::vector<int> chunk_ids;
+    for (long c = 0; c < nchunk; c++)
+        if (flags[c]) chunk_ids.push_back((int)c);
+    h->n_active_chunks = (long)chunk_ids.size();
+    while (chunk_ids.size() % 4 != 0 || chunk_ids.empty()) chunk_ids.push_back(-1);  // k_rho_tma reads groups of four
+    h->d_chunk_ids.upload(chunk_ids, st);
+    CK(cudaStreamSynchronize(st));
+    build_contract_schedule(h, h->n_active_chunks, nsm);
 }
 
 // Sort the (local point, source atom) pairs of the cross-atom interpolation into (atom, spline interval) bins.
@@ -355,6 +457,7 @@ void do_build(dftgrid* h) {
     h->d_dJ.alloc(nlp);
     h->d_dxc.zero(st);
     h->d_dJ.zero(st);
+    h->d_rho.zero(st);  // tiles of exact-zero amplitudes are skipped by k_rho_tma: their density stays 0
     // whole 128-row tiles / 32-row chunks must be readable by the bulk-copy producers: rows past nloc are zero
     h->d_phi.alloc((nl + kTileM - 1) / kTileM * kTileM * (size_t)h->nbp + 64);
     h->d_phi.zero(st);
@@ -371,83 +474,8 @@ void do_build(dftgrid* h) {
     h->d_coef.alloc((size_t)g.natoms * g.nrad * g.nlm * 4);
     h->d_res.alloc((size_t)2 * h->nbf * h->nbf + 2);
 
-    // ---- contraction tiling
-    const int nt = (h->nbp + kTileM - 1) / kTileM;
-    std::vector<int> pairs;
-    for (int i = 0; i < nt; i++)
-        for (int j = i; j < nt; j++) {
-            pairs.push_back(i);
-            pairs.push_back(j);
-        }
-    h->npairs = (int)pairs.size() / 2;
-    h->d_pairs.upload(pairs, st);
     int nsm = 148;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
-    {
-        // stream-K schedule of the [XC | J] contraction: equal DMMA cost per CTA, one CTA per SM
-        const long nchunk = (g.nloc + kTileK - 1) / kTileK;
-        const int nitems = 2 * h->npairs;
-        std::vector<int> cost(nitems);
-        long W = 0;
-        for (int it = 0; it < nitems; it++) {
-            const int ti = pairs[2 * (it % h->npairs)], tj = pairs[2 * (it % h->npairs) + 1];
-            // relative DMMA cost of one k-chunk of this tile pair (full off-diagonal 128x128 tile = 20): a 64-wide
-            // edge tile issues half the DMMAs but pays the same loads (measured ~0.6), a diagonal tile issues 24/32 (8/32 on the edge)
-            const char* nc = std::getenv("DFTGRID_NARROW_COST");
-            const char* dc = std::getenv("DFTGRID_DIAG_COST");
-            const bool narrow = std::min(kTileN, h->nbp - tj * kTileN) <= 64;
-            const int c_narrow = nc ? std::atoi(nc) : 11, c_diag = dc ? std::atoi(dc) : 15;
-            cost[it] = ti == tj ? (narrow ? 8 : c_diag) : (narrow ? c_narrow : 20);
-            W += (long)cost[it] * nchunk;
-        }
-        const int G = (int)std::max<long>(1, std::min<long>(nsm, W / 40 > 0 ? W / 40 : 1));
-        std::vector<ConSeg> segs;
-        std::vector<int> cta_off(1, 0), item_off(nitems + 1, 0);
-        int item = 0;
-        long cpos = 0;  // next unassigned chunk of `item`
-        long done = 0;  // cost units assigned so far
-        for (int c = 0; c < G; c++) {
-            const long target = W * (c + 1) / G;  // cumulative cost this CTA should reach
-            while (item < nitems && (done < target || c == G - 1)) {
-                long take = (target - done + cost[item] - 1) / cost[item];
-                if (c == G - 1) take = nchunk - cpos;
-                take = std::min(take, nchunk - cpos);
-                if (take > 0) {
-                    segs.push_back(ConSeg{item / h->npairs, item % h->npairs, (int)cpos, (int)(cpos + take)});
-                    cpos += take;
-                    done += take * cost[item];
-                }
-                if (cpos == nchunk) {
-                    item++;
-                    cpos = 0;
-                    item_off[item] = (int)segs.size();
-                } else if (c != G - 1) {
-                    break;
-                }
-            }
-            cta_off.push_back((int)segs.size());
-        }
-        for (int it = item + 1; it <= nitems; it++) item_off[it] = (int)segs.size();
-        if (nchunk == 0) {  // empty shard: every item still gets one (empty) segment so that the reduction writes zeros
-            segs.clear();
-            cta_off.assign(1, 0);
-            for (int it = 0; it < nitems; it++) {
-                item_off[it] = it;
-                segs.push_back(ConSeg{it / h->npairs, it % h->npairs, 0, 0});
-            }
-            item_off[nitems] = nitems;
-            cta_off.push_back(nitems);
-        }
-        h->con_ctas = (int)cta_off.size() - 1;
-        h->nsplit = (int)segs.size();
-        h->d_segs.alloc(segs.size());
-        CK(cudaMemcpyAsync(h->d_segs.p, segs.data(), segs.size() * sizeof(ConSeg), cudaMemcpyHostToDevice, st));
-        h->d_cta_off.upload(cta_off, st);
-        h->d_item_off.upload(item_off, st);
-        h->d_partial.alloc((size_t)segs.size() * kTileM * kTileN);
-        CK(cudaStreamSynchronize(st));  // the host vectors above go out of scope
-    }
-
     {
         // source-atom chunks of the interpolation kernel: enough CTAs for >= ~8 full waves (6 CTAs of 128 threads per SM)
         const long ctas = (g.nloc + 127) / 128, wave = 6L * nsm;
@@ -460,9 +488,7 @@ void do_build(dftgrid* h) {
 
     CK(cudaFuncSetAttribute(k_phi, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(((size_t)kPhiPts * (kPhiCols + 1) + (size_t)kPhiMaxExp * kPhiPts) * sizeof(double))));
-    CK(cudaFuncSetAttribute(k_rho, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRhoSmemBytes));
     CK(cudaFuncSetAttribute(k_rho_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRhoTmaSmemBytes));
-    CK(cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConSmemBytes));
     CK(cudaFuncSetAttribute(k_contract_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConTmaSmemBytes));
     const size_t becke_smem = (size_t)kBeckeWarps * 2 * g.natoms * sizeof(double);
     if (becke_smem > 200 * 1024) throw std::runtime_error("too many atoms for the Becke kernel's shared-memory layout");
@@ -558,6 +584,7 @@ void do_build(dftgrid* h) {
         h->launches++;
     }
     record(h, 3);
+    build_active_lists(h, nsm);
     build_pair_bins(h);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -574,11 +601,9 @@ void run_density(dftgrid* h) {
     const long nshell = (long)g.natoms * g.nrad;
     record(h, 4);
     if (g.nloc > 0) {
-        static const bool rho_cp_async = std::getenv("DFTGRID_RHO_CPASYNC") != nullptr;  // developer A/B switch
-        if (rho_cp_async)
-            k_rho<<<(unsigned)((g.nloc + kTileM - 1) / kTileM), kDenseThreads, kRhoSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_rho.p, g.nloc, h->nbp);
-        else
-            k_rho_tma<<<(unsigned)((g.nloc + kTileM - 1) / kTileM), kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_rho.p, g.nloc, h->nbp);
+        if (h->n_active_chunks > 0)
+            k_rho_tma<<<(unsigned)((h->n_active_chunks + 3) / 4), kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_chunk_ids.p, h->d_rho.p,
+                                                                                                     g.nloc, h->nbp);
         h->launches++;
     }
     record(h, 5);
@@ -691,13 +716,8 @@ void run_contract(dftgrid* h) {
     const GridShape& g = h->g;
     const size_t nb2 = (size_t)h->nbf * h->nbf;
     record(h, 12);
-    static const bool use_cp_async = std::getenv("DFTGRID_CONTRACT_CPASYNC") != nullptr;  // developer A/B switch
-    if (use_cp_async)
-        k_contract<<<h->con_ctas, kDenseThreads, kConSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_pairs.p, h->d_segs.p, h->d_cta_off.p,
-                                                                      h->d_partial.p, g.nloc, h->nbp);
-    else
-        k_contract_tma<<<h->con_ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_pairs.p, h->d_segs.p,
-                                                                              h->d_cta_off.p, h->d_partial.p, h->nbp);
+    k_contract_tma<<<h->con_ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p, h->d_pairs.p,
+                                                                          h->d_segs.p, h->d_cta_off.p, h->d_partial.p, h->nbp);
     k_contract_reduce<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 0.5,
                                                          h->d_res.p + nb2, h->d_res.p);
     h->launches += 2;
@@ -711,11 +731,13 @@ void run_contract(dftgrid* h) {
     h->timed_iter = h->have_potential;
 }
 
+// Zero-padded copy of the density matrix for k_rho_tma with the 32x32 diagonal blocks halved (exact; see
+// kernels_dense.cuh: the blocks above the diagonal are visited once and stand for both triangles).
 __global__ void k_pad_P(const double* __restrict__ Praw, double* __restrict__ P, int nb, int nbp) {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long)nb * nb) return;
     const int i = (int)(t / nb), j = (int)(t % nb);
-    P[(size_t)i * nbp + j] = Praw[t];
+    P[(size_t)i * nbp + j] = Praw[t] * (i / kTileK == j / kTileK ? 0.5 : 1.0);
 }
 
 // True when the caller's host buffer is page-locked (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor):
