@@ -92,7 +92,7 @@ __global__ void k_chunk_flags(const double* __restrict__ phi, long nchunk, int n
 // Warp tiling of the 128 x 128 slab tile: 4 warps along M (32 rows) x 2 along N; an N-warp owns two of the four
 // 32-column blocks, {0,3} and {1,2}, so that both do the same number of in-slab block-steps (5 each).
 constexpr int kRhoStageDoubles = kTileM * kLdK + kTileK * kLdN;
-constexpr int kRhoTmaThreads = kDenseThreads + 32;
+constexpr int kRhoTmaThreads = kDenseThreads + 128;  // 2 DMMA warpgroups + 1 producer warpgroup
 constexpr size_t kRhoTmaSmemBytes = (size_t)kStages * kRhoStageDoubles * sizeof(double) + 2 * kTileM * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
 
 __device__ __forceinline__ int rho_block_of(int wn, int half) { return wn == 0 ? (half == 0 ? 0 : 3) : (half == 0 ? 1 : 2); }
@@ -146,7 +146,9 @@ struct RhoStep {
 // grid = ceil(number of non-zero 32-point chunks / 4): a CTA's 128-row tile is made of four non-zero chunks
 // (chunk_ids, padded to a multiple of 4 with -1 = unused row group).  Ph: zero-padded [nbp][nbp] density matrix with
 // halved 32x32 diagonal blocks (k_pad_P).  rho of skipped chunks stays 0.
-// 9 warps: one SM sub-partition hosts 3 of them, so ptxas caps the kernel at 168 registers per thread.
+// 3 warpgroups: two of DMMA warps, one whose first warp is the producer.  384 threads start with 168 registers each;
+// the producer warpgroup hands its share back (setmaxnreg.dec) and the DMMA warpgroups grow to 232 (setmaxnreg.inc), so
+// the 128-register accumulator tile plus fragments and loop state never spill.
 __global__ void __launch_bounds__(kRhoTmaThreads, 1)
 k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const int* __restrict__ chunk_ids, double* __restrict__ rho, long nloc,
           int nbp) {
@@ -157,7 +159,7 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) {
-            mbar_init(full + s, 1);   // the producer's arrive.expect_tx
+            mbar_init(full + s, 4);   // one arrive.expect_tx per producer warp
             mbar_init(empty + s, 8);  // one arrival per DMMA warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -169,31 +171,33 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
     int total = 0;
     for (int J = 0; J < nslab; J++) total += nk - J * (kTileN / kTileK);
 
-    if (warp == 8) {
-        // ===== producer warp: per stage the 128 Phi row pieces (256 B each, four per lane) and 32 rows of the Ph block
+    if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        // ===== producer warps: warp 8+j copies, per stage, the 32 Phi row pieces (256 B each, one per lane) of row group j
+        // and 8 of the 32 rows of the Ph block.  A bulk copy costs the issuing warp ~50 clocks, so one warp alone
+        // (160 copies per stage) cannot keep up with the short in-slab steps.
+        const int j = warp - 8;
         RhoStep ld{0, 0, nbp};
-        const double* grp[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) grp[r] = phi + ((size_t)max(my_chunks[r], 0) * kTileK + lane) * (size_t)nbp;  // unused group: any valid rows
+        const double* grp = phi + ((size_t)max(my_chunks[j], 0) * kTileK + lane) * (size_t)nbp;  // unused group: any valid rows
         for (int it = 0; it < total; it++) {
             const unsigned stage = (unsigned)it % kStages, round = (unsigned)it / kStages;
             double* st = sm + (size_t)stage * kRhoStageDoubles;
             const int slab = ld.slab * kTileN, kc = ld.chunk() * kTileK;
             const unsigned wb = (unsigned)min(kTileN, nbp - slab) * 8u;
             mbar_wait(empty + stage, (round & 1u) ^ 1u);
-            if (lane == 0) mbar_arrive_expect_tx(full + stage, kTileM * kTileK * 8u + kTileK * wb);
+            if (lane == 0) mbar_arrive_expect_tx(full + stage, 32u * kTileK * 8u + 8u * wb);
             __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int row = lane + 32 * r;
-                bulk_copy_g2s(st + row * kLdK, grp[r] + kc, kTileK * 8u, full + stage);
+            bulk_copy_g2s(st + (32 * j + lane) * kLdK, grp + kc, kTileK * 8u, full + stage);
+            if (lane < 8) {
+                const int r = 8 * j + lane;
+                bulk_copy_g2s(st + kTileM * kLdK + r * kLdN, Ph + (size_t)(kc + r) * nbp + slab, wb, full + stage);
             }
-            bulk_copy_g2s(st + kTileM * kLdK + lane * kLdN, Ph + (size_t)(kc + lane) * nbp + slab, wb, full + stage);
             ld.advance();
         }
         return;
     }
     // ===== DMMA warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     const int wm = warp & 3, wn = warp >> 2;
     const int g = lane >> 2, q = lane & 3;
     const int blk0 = rho_block_of(wn, 0), blk1 = rho_block_of(wn, 1);
