@@ -127,14 +127,19 @@ __device__ __forceinline__ void rho_mma_stage(const double* st, double (&acc)[4]
     }
 }
 
-// Steps of one CTA: for slab J = 0.., the k-chunks 4J .. nk-1 in ascending order.
+// Steps of one CTA: for slab J = 0.., first the k-chunks past the slab (ascending), then the slab's own chunks in
+// DESCENDING order: own chunk `rel` feeds the column blocks <= rel, so after that step block `rel` is complete, and the
+// chunk's Phi tile in shared memory holds exactly the amplitudes of that block's columns for the row-dot epilogue.
 struct RhoStep {
     int slab, i, nbp;
     __device__ __forceinline__ int nk() const { return nbp / kTileK; }
     __device__ __forceinline__ int first_chunk() const { return slab * (kTileN / kTileK); }
     __device__ __forceinline__ int count() const { return nk() - first_chunk(); }
-    __device__ __forceinline__ int chunk() const { return first_chunk() + i; }
-    __device__ __forceinline__ int nblk() const { return min(kTileN / kTileK, nk() - first_chunk()); }  // 32-column blocks in the slab
+    __device__ __forceinline__ int nblk() const { return min(kTileN / kTileK, count()); }  // 32-column blocks in the slab
+    __device__ __forceinline__ int outer() const { return count() - nblk(); }
+    // own-chunk index inside the slab (nblk-1 .. 0), or -1 for a chunk past the slab
+    __device__ __forceinline__ int rel() const { return i < outer() ? -1 : nblk() - 1 - (i - outer()); }
+    __device__ __forceinline__ int chunk() const { return i < outer() ? first_chunk() + nblk() + i : first_chunk() + rel(); }
     __device__ __forceinline__ void advance() {
         if (++i == count()) {
             i = 0;
@@ -215,8 +220,9 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
 #pragma unroll
                 for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
         }
-        // inside the slab's own k-range chunk i feeds the column blocks <= i only
-        const bool h0 = blk0 < nblk && blk0 <= cs.i, h1 = blk1 < nblk && blk1 <= cs.i;
+        // a chunk past the slab feeds every column block, the slab's own chunk `rel` the blocks <= rel
+        const int rel = cs.rel();
+        const bool h0 = blk0 < nblk && (rel < 0 || blk0 <= rel), h1 = blk1 < nblk && (rel < 0 || blk1 <= rel);
         mbar_wait(full + stage, round & 1u);
         const double* st = sm + (size_t)stage * kRhoStageDoubles;
         if (h0 && h1)
@@ -225,28 +231,31 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
             rho_mma_stage<true, false>(st, acc, wm, blk0 * 32, blk1 * 32, lane);
         else if (h1)
             rho_mma_stage<false, true>(st, acc, wm, blk0 * 32, blk1 * 32, lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + stage);
-        if (cs.i == cs.count() - 1) {
-            // epilogue of this column slab: rowsum += T''[p][n] * Phi[p][n]
-            const int slab = cs.slab * kTileN;
+        if (rel >= 0 && (rel == blk0 || rel == blk1)) {
+            // block `rel` is complete: rowsum += T''[p][n] * Phi[p][n] with Phi[p][slab + 32 rel ..] = this stage's Phi tile
+            const double* As = st + (wm * 32 + g) * kLdK + q * 2;
+            if (rel == blk0) {
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++) {
-                const long p = p0w + mt * 8 + g;
-                if (my_chunk >= 0 && p < nloc) {
+                for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-                    for (int nt = 0; nt < 8; nt++) {
-                        const int blk = nt < 4 ? blk0 : blk1;
-                        if (blk < nblk) {
-                            const int col = slab + blk * 32 + (nt & 3) * 8 + q * 2;
-                            const double2 f = *reinterpret_cast<const double2*>(phi + p * (long)nbp + col);
-                            rowsum[mt] = fma(acc[mt][nt][0], f.x, rowsum[mt]);
-                            rowsum[mt] = fma(acc[mt][nt][1], f.y, rowsum[mt]);
-                        }
+                    for (int j = 0; j < 4; j++) {
+                        const double2 f = *reinterpret_cast<const double2*>(As + mt * 8 * kLdK + j * 8);
+                        rowsum[mt] = fma(acc[mt][j][0], f.x, rowsum[mt]);
+                        rowsum[mt] = fma(acc[mt][j][1], f.y, rowsum[mt]);
                     }
-                }
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const double2 f = *reinterpret_cast<const double2*>(As + mt * 8 * kLdK + j * 8);
+                        rowsum[mt] = fma(acc[mt][4 + j][0], f.x, rowsum[mt]);
+                        rowsum[mt] = fma(acc[mt][4 + j][1], f.y, rowsum[mt]);
+                    }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);
         cs.advance();
     }
     // reduce over the 4 lanes of a quad, then over the two N-warps
