@@ -319,7 +319,7 @@ def main():
     con_ms = max_over_ranks(phases["contract"])
     peaks, peak_kind = measured_peaks()
     ach = flops_contract / (con_ms * 1e-3) / 1e12
-    roof = {"kernel": "k_contract (+k_contract_reduce)", "bound": "tensor", "achieved": ach, "peak": FP64_TENSOR_PEAK_TFLOPS,
+    roof = {"kernel": "k_contract_tma (+k_contract_reduce)", "bound": "tensor", "achieved": ach, "peak": FP64_TENSOR_PEAK_TFLOPS,
             "unit": "TFLOP/s", "frac": ach / FP64_TENSOR_PEAK_TFLOPS, "traffic": None,
             "peak_source": "FP64 DMMA peak measured on this pool with tools/microbench/fp64_peak.cu (MEASURED_PEAKS.json has no FP64 entry; "
                            "its HBM figure %s GB/s is the denominator for the streaming kernels, %s)" % (peaks.get("hbm_gbs"), peak_kind),
