@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--workload", default="h2o64")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="multi-GPU: sum [J | XC] with ncclAllReduce instead of the peer-memory kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -256,6 +257,12 @@ def main():
     t0 = time.time()
     g.create_grid(comm_id)
     build_wall = time.time() - t0
+    peer_path = False
+    if world > 1 and not args.no_peer:
+        # the [J | XC] sum runs in the library's own peer-memory kernels when the ranks' GPUs have a P2P path
+        hs = [None] * world
+        dist.all_gather_object(hs, g.peer_export())
+        peer_path = g.peer_connect(hs)
     tb = g.timings()
     P = systems.synthetic_density(mol)
     flush = None
@@ -338,6 +345,9 @@ def main():
                "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(mol.nbf ** 2 * 8),
                        "d2h_bytes_per_step": int((2 * mol.nbf ** 2 + 2) * 8)},
                "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
+               "collectives": ("none (single GPU)" if world == 1 else
+                               "shell sums + rho_lm: ncclAllReduce; [J | XC]: " + ("peer-memory kernels (k_contract_reduce_publish + k_peer_sum)"
+                                                                                  if peer_path else "ncclAllReduce")),
                "phases_ms": {k: round(v, 4) for k, v in phases.items()},
                "grid_build": {"wall_s": round(build_wall, 3), "becke_ms": tb["becke"], "phi_ms": tb["phi"],
                               "phi_gridpt_basis_evals_per_s": g.nloc * mol.nbf / (tb["phi"] * 1e-3) * world if tb["phi"] > 0 else None,

@@ -18,6 +18,7 @@
 #include "kernels_dense.cuh"
 #include "kernels_grid.cuh"
 #include "kernels_hartree.cuh"
+#include "kernels_peer.cuh"
 #include "nccl_dyn.h"
 
 using namespace dfg;
@@ -117,6 +118,13 @@ struct dftgrid {
 
     // comm
     NcclComm comm = nullptr;
+    // peer-memory reduction of [J | XC] (kernels_peer.cuh)
+    unsigned char* xbuf = nullptr;        // this rank's exchange buffer
+    size_t xbuf_bytes = 0;
+    PeerSet peers{};
+    std::vector<void*> peer_mapped;       // cudaIpcOpenMemHandle results to close
+    bool peer_ready = false;
+    unsigned long long peer_epoch = 0;
 
     // timing
     cudaEvent_t ev[16]{};
@@ -125,6 +133,8 @@ struct dftgrid {
     double t_ms[DFTGRID_T_COUNT]{};
 
     ~dftgrid() {
+        for (void* m : peer_mapped) cudaIpcCloseMemHandle(m);
+        if (xbuf) cudaFree(xbuf);
         if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
@@ -718,14 +728,28 @@ void run_contract(dftgrid* h) {
     record(h, 12);
     k_contract_tma<<<h->con_ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p, h->d_pairs.p,
                                                                           h->d_segs.p, h->d_cta_off.p, h->d_partial.p, h->nbp);
-    k_contract_reduce<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 0.5,
-                                                         h->d_res.p + nb2, h->d_res.p);
+    if (h->peer_ready) {
+        // split-K reduction straight into this rank's exchange buffer, then the cross-rank sum over peer memory
+        h->peer_epoch++;
+        k_contract_reduce_publish<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp,
+                                                                     1.0, 0.5, h->peers, h->peer_epoch);
+    } else {
+        k_contract_reduce<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 0.5,
+                                                             h->d_res.p + nb2, h->d_res.p);
+    }
     h->launches += 2;
     // exc and nel come from the already-reduced shell sums (identical on every rank): appended after the reduced block
     CK(cudaMemcpyAsync(h->d_res.p + 2 * nb2, h->d_scalars.p + 2, sizeof(double), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(h->d_res.p + 2 * nb2 + 1, h->d_scalars.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, st));
     record(h, 13);
-    allreduce(h, h->d_res.p, 2 * nb2);
+    if (h->peer_ready) {
+        const size_t n = 2 * nb2;
+        const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 296);
+        k_peer_sum<<<blocks, 256, 0, st>>>(h->peers, h->peer_epoch, n, h->d_res.p);
+        h->launches++;
+    } else {
+        allreduce(h, h->d_res.p, 2 * nb2);
+    }
     record(h, 14);
     h->contract_valid = h->have_potential;
     h->timed_iter = h->have_potential;
@@ -791,6 +815,14 @@ int guarded(F&& f) {
 }
 
 void use_device(dftgrid* h) { CK(cudaSetDevice(h->device)); }
+
+// After a stream synchronisation: a bounded spin-wait of the peer-memory reduction that gave up leaves a flag behind.
+void check_peer_error(dftgrid* h) {
+    if (!h->peer_ready) return;
+    unsigned long long err = 0;
+    CK(cudaMemcpy(&err, h->xbuf + offsetof(PeerHeader, error), sizeof err, cudaMemcpyDeviceToHost));
+    if (err) throw std::runtime_error("peer-memory reduction timed out waiting for another rank");
+}
 
 template <typename T>
 void download(dftgrid* h, const DevBuf<T>& b, T* out, size_t count) {
@@ -878,6 +910,58 @@ int dftgrid_comm_init(dftgrid_t* h, const void* id128) {
     });
 }
 
+int dftgrid_peer_export(dftgrid_t* h, void* handle64) {
+    return guarded([&] {
+        use_device(h);
+        if (!handle64) throw std::runtime_error("null argument");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+        if (h->nranks < 2 || h->nranks > kPeerMaxRanks) throw std::runtime_error("peer reduction needs 2..16 ranks");
+        if (!h->xbuf) {
+            const size_t nb2 = (size_t)h->nbf * h->nbf;
+            h->xbuf_bytes = kPeerHeaderBytes + 2 * (2 * nb2) * sizeof(double);
+            CK(cudaMalloc(&h->xbuf, h->xbuf_bytes));
+            CK(cudaMemset(h->xbuf, 0, h->xbuf_bytes));
+        }
+        cudaIpcMemHandle_t hd;
+        CK(cudaIpcGetMemHandle(&hd, h->xbuf));
+        std::memcpy(handle64, &hd, sizeof hd);
+    });
+}
+
+int dftgrid_peer_connect(dftgrid_t* h, const void* handles) {
+    return guarded([&] {
+        use_device(h);
+        if (!handles) throw std::runtime_error("null argument");
+        if (!h->xbuf) throw std::runtime_error("dftgrid_peer_export has not been called");
+        if (h->peer_ready) return;
+        PeerSet ps{};
+        ps.nranks = h->nranks;
+        ps.rank = h->rank;
+        for (int r = 0; r < h->nranks; r++) {
+            if (r == h->rank) {
+                ps.base[r] = h->xbuf;
+                continue;
+            }
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, (const char*)handles + (size_t)r * sizeof hd, sizeof hd);
+            void* m = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&m, hd, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                for (void* q : h->peer_mapped) cudaIpcCloseMemHandle(q);
+                h->peer_mapped.clear();
+                throw std::runtime_error(std::string("cudaIpcOpenMemHandle failed (no P2P path between the ranks' GPUs?): ") + cudaGetErrorString(e));
+            }
+            h->peer_mapped.push_back(m);
+            ps.base[r] = (unsigned char*)m;
+        }
+        h->peers = ps;
+        h->peer_ready = true;
+    });
+}
+
+int dftgrid_peer_active(const dftgrid_t* h) { return h->peer_ready ? 1 : 0; }
+
 int dftgrid_build(dftgrid_t* h) {
     return guarded([&] {
         use_device(h);
@@ -918,6 +1002,7 @@ int dftgrid_hartree_J(dftgrid_t* h, double* J) {
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h->h_res, h->d_res.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        check_peer_error(h);
         std::memcpy(J, h->h_res, nb2 * sizeof(double));
     });
 }
@@ -935,6 +1020,7 @@ int dftgrid_xc(dftgrid_t* h, double* XC, double* exc) {
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h->h_res, h->d_res.p + nb2, (nb2 + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        check_peer_error(h);
         if (XC) std::memcpy(XC, h->h_res, nb2 * sizeof(double));
         if (exc) *exc = h->h_res[nb2];
     });
@@ -973,6 +1059,7 @@ int dftgrid_download_results(dftgrid_t* h, double* J, double* XC, double* exc, d
         if (XC && !dx) CK(cudaMemcpyAsync(h->h_res + nb2, h->d_res.p + nb2, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(h->h_res + 2 * nb2, h->d_res.p + 2 * nb2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        check_peer_error(h);
         if (J && !dj) std::memcpy(J, h->h_res, nb2 * sizeof(double));
         if (XC && !dx) std::memcpy(XC, h->h_res + nb2, nb2 * sizeof(double));
         if (exc) *exc = h->h_res[2 * nb2];

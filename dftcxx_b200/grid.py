@@ -45,6 +45,9 @@ def lib():
     L.dftgrid_destroy.restype = None
     L.dftgrid_comm_unique_id.argtypes = [C.c_void_p]
     L.dftgrid_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    L.dftgrid_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.dftgrid_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
+    L.dftgrid_peer_active.argtypes = [C.c_void_p]
     L.dftgrid_timer_stop.argtypes = [C.c_void_p, _dp]
     for n in ("dftgrid_build", "dftgrid_iteration_device", "dftgrid_synchronize", "dftgrid_timer_start"):
         getattr(L, n).argtypes = [C.c_void_p]
@@ -140,6 +143,22 @@ class MolecularGrid:
         self.point_offset = lib().dftgrid_point_offset(self.h)
         self.nlm = lib().dftgrid_nlm(self.h)
         self.nang = LEBEDEV_COUNTS[self.lebedev_order]
+
+    # -- peer-memory reduction (multi-GPU, optional) --------------------------------------------------------
+    def peer_export(self):
+        """This rank's 64-byte CUDA IPC handle of its [J | XC] exchange buffer (dftgrid_peer_export)."""
+        buf = C.create_string_buffer(64)
+        self._ck(lib().dftgrid_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, handles):
+        """handles: every rank's peer_export() blob in rank order.  Returns True when the peer path is active; on a
+        mapping failure (no P2P path) the library keeps using NCCL and False is returned."""
+        blob = b"".join(handles)
+        if len(blob) != 64 * self.nranks:
+            raise GridError("peer_connect needs one 64-byte handle per rank")
+        rc = lib().dftgrid_peer_connect(self.h, blob)
+        return rc == 0 and lib().dftgrid_peer_active(self.h) == 1
 
     def set_density(self, P):
         """set_density + correct_densities (src/moleculargrid.cpp:48-53,132-146)."""

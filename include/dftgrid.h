@@ -73,6 +73,17 @@ int dftgrid_shard_range(long nshell_total, int rank, int nranks, long* first_she
 int dftgrid_comm_unique_id(void* id128);
 int dftgrid_comm_init(dftgrid_t* h, const void* id128);
 
+/* Optional peer-memory path for the last collective of an iteration (nranks 2..16, one process per GPU, GPUs with a P2P
+ * path — NVLink / NVSwitch): the sum of the ranks' [J | XC] partial matrices is then done by the library's own kernels
+ * reading the other ranks' buffers directly (k_contract_reduce_publish + k_peer_sum) instead of ncclAllReduce; same
+ * rank-ordered sum on every rank, so results stay bit-identical across ranks.  dftgrid_peer_export writes this rank's
+ * 64-byte CUDA IPC handle; the host gathers all ranks' handles (rank order, 64 bytes each) and hands them to
+ * dftgrid_peer_connect on every rank.  Without these calls, or if the mapping fails, NCCL is used.  (No reference
+ * counterpart: the reference is single-process.) */
+int dftgrid_peer_export(dftgrid_t* h, void* handle64);
+int dftgrid_peer_connect(dftgrid_t* h, const void* handles /* [nranks][64] */);
+int dftgrid_peer_active(const dftgrid_t* h);
+
 /* MolecularGrid::create_grid (src/moleculargrid.cpp:193-261): points, quadrature weights, CGF amplitudes,
  * Becke weights; also factorises the radial Poisson operators used by dftgrid_hartree_J. */
 int dftgrid_build(dftgrid_t* h);

@@ -56,7 +56,19 @@ def parity(name):
     mg = G.MolecularGrid(system_from_golden(g), device=local, rank=rank, nranks=world)
     mg.set_grid_parameters(*grid_params(g))
     mg.create_grid(box[0])
-    J, XC, exc, nel = mg.iteration(g["P"])
+    J, XC, exc, nel = mg.iteration(g["P"])  # last collective through ncclAllReduce
+    peer = False
+    if os.environ.get("DFTGRID_TEST_PEER", "1") == "1":
+        hs = [None] * world
+        dist.all_gather_object(hs, mg.peer_export())
+        peer = mg.peer_connect(hs)
+        for _ in range(3):  # several epochs: the exchange buffers alternate and are re-used
+            Jp, XCp, excp, nelp = mg.iteration(g["P"])
+        # the NCCL ring/tree and the rank-ordered peer sum may round differently; both are within the parity tolerance
+        peer_close = bool(np.max(np.abs(Jp - J)) <= 1e-12 and np.max(np.abs(XCp - XC)) <= 1e-12 and excp == exc and nelp == nel)
+        J, XC = Jp, XCp
+    else:
+        peer_close = True
     # the sharded points are the matching slice of the single-rank grid
     idx = g["idx"]
     mine = (idx >= mg.point_offset) & (idx < mg.point_offset + mg.nloc)
@@ -70,8 +82,9 @@ def parity(name):
     if rank == 0:
         same = all(torch.equal(a, allr[0]) for a in allr)
         dJ, dXC = np.max(np.abs(J - g["J"])), np.max(np.abs(XC - g["XC"]))
-        good = same and flags.item() == 1.0 and dJ <= 1e-10 and dXC <= 1e-10 and abs(exc - float(g["exc"])) <= 1e-10 and abs(nel - float(g["nel"])) <= 1e-9
-        print("PARITY_%s world=%d dJ=%.2e dXC=%.2e identical_on_all_ranks=%s shard_ok=%s" % ("OK" if good else "FAIL", world, dJ, dXC, same, flags.item() == 1.0))
+        good = same and peer_close and flags.item() == 1.0 and dJ <= 1e-10 and dXC <= 1e-10 and abs(exc - float(g["exc"])) <= 1e-10 and abs(nel - float(g["nel"])) <= 1e-9
+        print("PARITY_%s world=%d dJ=%.2e dXC=%.2e identical_on_all_ranks=%s shard_ok=%s peer_path=%s peer_vs_nccl_ok=%s" % (
+            "OK" if good else "FAIL", world, dJ, dXC, same, flags.item() == 1.0, peer, peer_close))
     mg.close()
     dist.destroy_process_group()
 
