@@ -731,10 +731,10 @@ void run_contract(dftgrid* h) {
     if (h->peer_ready) {
         // split-K reduction straight into this rank's exchange buffer, then the cross-rank sum over peer memory
         h->peer_epoch++;
-        k_contract_reduce_publish<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp,
+        k_contract_reduce_publish<<<dim3(h->npairs, 2, kReduceSplit), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp,
                                                                      1.0, 0.5, h->peers, h->peer_epoch);
     } else {
-        k_contract_reduce<<<dim3(h->npairs, 2), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 0.5,
+        k_contract_reduce<<<dim3(h->npairs, 2, kReduceSplit), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 0.5,
                                                              h->d_res.p + nb2, h->d_res.p);
     }
     h->launches += 2;

@@ -493,7 +493,9 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
 }
 
 // out0/out1: nb x nb (symmetric => row/column-major agnostic).  Each thread sums one element over the item's partial
-// tiles [item_slot_off[item], item_slot_off[item+1]) in order.  grid = (npairs, 2).
+// tiles [item_slot_off[item], item_slot_off[item+1]) in order.  grid = (npairs, 2, kReduceSplit): the tile's elements
+// are split over blockIdx.z so that a small basis (one or two tile pairs) still fills the machine.
+constexpr int kReduceSplit = 16;
 __global__ void k_contract_reduce(const double* __restrict__ partial, const int* __restrict__ pair_ij, const int* __restrict__ item_slot_off,
                                   int npairs, int nb, int nbp, double scale0, double scale1, double* __restrict__ out0, double* __restrict__ out1) {
     const int pair = blockIdx.x, z = blockIdx.y;
@@ -502,7 +504,8 @@ __global__ void k_contract_reduce(const double* __restrict__ partial, const int*
     const int k0 = item_slot_off[item], k1 = item_slot_off[item + 1];
     double* out = z == 0 ? out0 : out1;
     const double scale = z == 0 ? scale0 : scale1;
-    for (int e = threadIdx.x; e < kTileM * kTileN; e += blockDim.x) {
+    constexpr int per_z = kTileM * kTileN / kReduceSplit;
+    for (int e = blockIdx.z * per_z + threadIdx.x; e < (blockIdx.z + 1) * per_z; e += blockDim.x) {
         const int r = e / kTileN, c = e % kTileN;
         const int gi = ti * kTileM + r, gj = tj * kTileN + c;
         if (gi >= nb || gj >= nb) continue;

@@ -62,7 +62,7 @@ __device__ __forceinline__ bool peer_wait_all(const PeerSet& ps, bool consumed_f
     return true;
 }
 
-// grid = (npairs, 2) as k_contract_reduce.  n = 2 nb^2.
+// grid = (npairs, 2, kReduceSplit) as k_contract_reduce.
 __global__ void k_contract_reduce_publish(const double* __restrict__ partial, const int* __restrict__ pair_ij, const int* __restrict__ item_slot_off,
                                           int npairs, int nb, int nbp, double scale_xc, double scale_j, PeerSet ps, unsigned long long epoch) {
     __shared__ bool ok;
@@ -81,7 +81,8 @@ __global__ void k_contract_reduce_publish(const double* __restrict__ partial, co
     const int k0 = item_slot_off[item], k1 = item_slot_off[item + 1];
     double* out = z == 0 ? contrib + nb2 : contrib;  // res layout [J | XC]; item z = 0 is XC
     const double scale = z == 0 ? scale_xc : scale_j;
-    for (int e = threadIdx.x; e < kTileM * kTileN; e += blockDim.x) {
+    constexpr int per_z = kTileM * kTileN / kReduceSplit;
+    for (int e = blockIdx.z * per_z + threadIdx.x; e < (blockIdx.z + 1) * per_z; e += blockDim.x) {
         const int r = e / kTileN, c = e % kTileN;
         const int gi = ti * kTileM + r, gj = tj * kTileN + c;
         if (gi >= nb || gj >= nb) continue;
@@ -96,7 +97,7 @@ __global__ void k_contract_reduce_publish(const double* __restrict__ partial, co
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
         if (atomicAdd(&me->ticket[0], 1u) == total - 1) {
             me->ticket[0] = 0u;
             __threadfence_system();
