@@ -101,6 +101,7 @@ struct dftgrid {
     // device: per iteration
     DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
     DevBuf<int> d_pairs, d_cta_off, d_item_off, d_chunk_ids;
+    int con_bc = 1;
     long n_active_chunks = 0;
     DevBuf<ConSeg> d_segs;
     int npairs = 0, nsplit = 1, con_ctas = 1, interp_chunks = 1;
@@ -224,8 +225,9 @@ float elapsed(dftgrid* h, int a, int b) {
     return ms;
 }
 
-// Stream-K schedule of the [XC | J] contraction over `nchunk` (non-zero) 32-point chunks: equal DMMA cost per CTA,
-// one CTA per SM.
+// Stream-K schedule of the [XC | J] contraction (see kernels_dense.cuh): the items' costs for ONE chunk are laid end to
+// end and cut into equal shares, one per CTA (one CTA per SM); a share is 1-3 segments given as fixed-point fractions
+// of the item's chunks (which chunks those are is decided on the device by a low-discrepancy hash).
 void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
     cudaStream_t st = h->stream;
     std::vector<int> pairs;
@@ -238,8 +240,8 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
     h->npairs = (int)pairs.size() / 2;
     h->d_pairs.upload(pairs, st);
     const int nitems = 2 * h->npairs;
-    std::vector<int> cost(nitems);
-    long W = 0;
+    std::vector<double> cost(nitems);
+    double W1 = 0.0;  // cost of all items for one chunk
     for (int it = 0; it < nitems; it++) {
         const int ti = pairs[2 * (it % h->npairs)], tj = pairs[2 * (it % h->npairs) + 1];
         // relative cost of one k-chunk of this tile pair (full off-diagonal 128x128 tile = 20): a 64-wide edge tile
@@ -250,45 +252,66 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
         const bool narrow = std::min(kTileN, h->nbp - tj * kTileN) <= 64;
         const int c_narrow = nc ? std::atoi(nc) : 11, c_diag = dc ? std::atoi(dc) : 12;
         cost[it] = ti == tj ? (narrow ? 8 : c_diag) : (narrow ? c_narrow : 20);
-        W += (long)cost[it] * nchunk;
+        W1 += cost[it];
     }
-    const int G = (int)std::max<long>(1, std::min<long>(nsm, W / 40 > 0 ? W / 40 : 1));
+    // block length (the period at which a CTA with several segments alternates between them): ~120 MB of Phi rows.
+    // Measured at (H2O)64: DRAM reads 15.1 GB without blocks, 9.8 GB with 80-160 MB blocks, 10.3 GB at 40 MB where the
+    // accumulator parking starts to cost time; at least 64 chunks; one block when the shard is smaller.
+    {
+        const double chunk_bytes = (double)kTileK * h->nbp * sizeof(double);
+        double l2_mb = 120.0;
+        if (const char* e = std::getenv("DFTGRID_L2_BLOCK_MB")) l2_mb = std::atof(e);  // developer sweep; <= 0: one block
+        long bc = l2_mb > 0 ? (long)(l2_mb * 1e6 / chunk_bytes) : nchunk;
+        bc = std::max<long>(bc, 64);
+        if (bc >= nchunk) bc = std::max<long>(nchunk, 1);
+        const long nblock = (nchunk + bc - 1) / bc;
+        if (nblock > 0) bc = (nchunk + nblock - 1) / nblock;  // equal blocks
+        h->con_bc = (int)bc;
+    }
+    const double W = W1 * (double)nchunk;
+    const int G = (int)std::max<long>(1, std::min<long>(nsm, (long)(W / 40.0) > 0 ? (long)(W / 40.0) : 1));
     std::vector<ConSeg> segs;
     std::vector<int> cta_off(1, 0), item_off(nitems + 1, 0);
-    int item = 0;
-    long cpos = 0;  // next unassigned chunk of `item`
-    long done = 0;  // cost units assigned so far
-    for (int c = 0; c < G; c++) {
-        const long target = W * (c + 1) / G;  // cumulative cost this CTA should reach
-        while (item < nitems && (done < target || c == G - 1)) {
-            long take = (target - done + cost[item] - 1) / cost[item];
-            if (c == G - 1) take = nchunk - cpos;
-            take = std::min(take, nchunk - cpos);
-            if (take > 0) {
-                segs.push_back(ConSeg{item / h->npairs, item % h->npairs, (int)cpos, (int)(cpos + take)});
-                cpos += take;
-                done += take * cost[item];
+    // cumulative cost positions: item `it` occupies [start[it], start[it] + cost[it]) of [0, W1)
+    {
+        int it = 0;
+        double start = 0.0;
+        for (int c = 0; c < G; c++) {
+            const double lo = W1 * c / G, hi = c == G - 1 ? W1 : W1 * (c + 1) / G;
+            // items overlapping [lo, hi)
+            while (it < nitems && start + cost[it] <= lo) {
+                start += cost[it];
+                it++;
             }
-            if (cpos == nchunk) {
-                item++;
-                cpos = 0;
-                item_off[item] = (int)segs.size();
-            } else if (c != G - 1) {
-                break;
+            int j = it;
+            double sj = start;
+            // position x inside item j as a 31-bit fixed-point fraction of the item's chunks; the same value for the
+            // share that ends at x and the share that starts there
+            auto frac = [&](double x, double s0, double cj) -> unsigned {
+                if (x <= s0) return 0u;
+                if (x >= s0 + cj) return 0x80000000u;
+                return (unsigned)((x - s0) / cj * 2147483648.0);
+            };
+            while (j < nitems && sj < hi) {
+                const unsigned tb = frac(lo, sj, cost[j]), te = frac(hi, sj, cost[j]);
+                if (te > tb) segs.push_back(ConSeg{j / h->npairs, j % h->npairs, tb, te});
+                sj += cost[j];
+                j++;
             }
+            cta_off.push_back((int)segs.size());
         }
-        cta_off.push_back((int)segs.size());
     }
-    for (int it = item + 1; it <= nitems; it++) item_off[it] = (int)segs.size();
-    if (nchunk == 0) {  // empty shard: every item still gets one (empty) segment so that the reduction writes zeros
-        segs.clear();
-        cta_off.assign(1, 0);
+    // A boundary W1*c/G is the same double for the share ending there and the share starting there, and the item starts
+    // are exact sums of small integers, so fe of one segment == fb of the next bit for bit.  Segments are emitted CTA
+    // after CTA in item-major order, hence an item's segments are consecutive: item_off indexes `segs` directly.
+    {
+        int pos = 0;
         for (int it = 0; it < nitems; it++) {
-            item_off[it] = it;
-            segs.push_back(ConSeg{it / h->npairs, it % h->npairs, 0, 0});
+            item_off[it] = pos;
+            while (pos < (int)segs.size() && segs[pos].z * h->npairs + segs[pos].pair == it) pos++;
         }
-        item_off[nitems] = nitems;
-        cta_off.push_back(nitems);
+        item_off[nitems] = pos;
+        if (pos != (int)segs.size()) throw std::runtime_error("internal error: contraction segments are not item-major");
     }
     h->con_ctas = (int)cta_off.size() - 1;
     h->nsplit = (int)segs.size();
@@ -727,7 +750,7 @@ void run_contract(dftgrid* h) {
     const size_t nb2 = (size_t)h->nbf * h->nbf;
     record(h, 12);
     k_contract_tma<<<h->con_ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p, h->d_pairs.p,
-                                                                          h->d_segs.p, h->d_cta_off.p, h->d_partial.p, h->nbp);
+                                                                          h->d_segs.p, h->d_cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc);
     if (h->peer_ready) {
         // split-K reduction straight into this rank's exchange buffer, then the cross-rank sum over peer memory
         h->peer_epoch++;

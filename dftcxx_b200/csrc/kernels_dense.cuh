@@ -304,16 +304,6 @@ __device__ __forceinline__ void con_mma_stage(const double* st, double (&acc)[32
     }
 }
 
-template <int MT, int NT>
-__device__ __forceinline__ void con_store(double* out, const double (&acc)[32][2], int warp, int lane) {
-    const int g = lane >> 2, q = lane & 3;
-#pragma unroll
-    for (int mt = 0; mt < MT; mt++)
-#pragma unroll
-        for (int nt = 0; nt < NT; nt++)
-            *reinterpret_cast<double2*>(out + (warp * (MT * 8) + mt * 8 + g) * kTileN + nt * 8 + q * 2) =
-                make_double2(acc[mt * NT + nt][0], acc[mt * NT + nt][1]);
-}
 
 // Diagonal tile pair (ti == tj), full 128 wide: only the 8x8 DMMA tiles on or above the diagonal are needed.  Warp W
 // owns row tile W (against column tiles W..15) and row tile 15-W (against column tiles 15-W..15): 17 DMMAs per
@@ -342,18 +332,6 @@ __device__ __forceinline__ void con_mma_stage_tri(const double* st, double (&acc
     }
 }
 
-template <int W>
-__device__ __forceinline__ void con_store_tri(double* out, const double (&acc)[32][2], int lane) {
-    const int g = lane >> 2, q = lane & 3;
-    constexpr int NB = 16 - W;
-#pragma unroll
-    for (int c = 0; c < NB; c++)
-        *reinterpret_cast<double2*>(out + (W * 8 + g) * kTileN + (W + c) * 8 + q * 2) = make_double2(acc[c][0], acc[c][1]);
-#pragma unroll
-    for (int c = 15 - W; c < 16; c++)
-        *reinterpret_cast<double2*>(out + ((15 - W) * 8 + g) * kTileN + c * 8 + q * 2) =
-            make_double2(acc[NB + c - (15 - W)][0], acc[NB + c - (15 - W)][1]);
-}
 
 // 64-wide diagonal edge tile: warp w owns row tile w against the 8 column tiles (the tile is 1 of ~28 pairs).
 __device__ __forceinline__ void con_mma_stage_diag_edge(const double* st, double (&acc)[32][2], int warp, int lane) {
@@ -372,21 +350,37 @@ __device__ __forceinline__ void con_mma_stage_diag_edge(const double* st, double
     }
 }
 
-__device__ __forceinline__ void con_store_diag_edge(double* out, const double (&acc)[32][2], int warp, int lane) {
-    const int g = lane >> 2, q = lane & 3;
-#pragma unroll
-    for (int nt = 0; nt < 8; nt++)
-        *reinterpret_cast<double2*>(out + (warp * 8 + g) * kTileN + nt * 8 + q * 2) = make_double2(acc[nt][0], acc[nt][1]);
+
+// Work decomposition ("stream-K", L2-friendly).  For ONE chunk the (matrix z, tile pair) items, weighted by their DMMA
+// cost, are laid end to end and cut into one equal share per CTA (one CTA per SM); a share is 1-3 segments
+// (z, pair, [tb, te)) where tb/te are 31-bit fixed-point FRACTIONS of the item's chunks.  Which chunks a fraction range
+// means is decided by a low-discrepancy hash: chunk position x belongs to the segment with tb <= u(x) < te,
+// u(x) = (x * 2654435769 mod 2^32) >> 1 (golden-ratio sequence).  Every CTA walks its chunks in ascending x, and since
+// every fraction range receives its chunks evenly spread over x, all CTAs advance through the Phi rows at the same pace:
+// a row is fetched from HBM by the first CTA that needs it and its other ~13 uses (7 tile pairs x 2 matrices) hit the
+// L2 a few microseconds later.  A CTA whose share crosses an item boundary (2-3 segments) alternates between its
+// segments once per block of `bc` chunks (~40 MB of Phi rows, L2-resident) and parks the inactive accumulators in the
+// segment's partial tile.  One partial tile per segment; k_contract_reduce adds an item's partial tiles in a fixed
+// order.  The schedule is built on the host (dftgrid_api.cu).
+struct ConSeg {
+    int z, pair;
+    unsigned tb, te;  // [tb, te) in units of 2^-31
+};
+
+__device__ __forceinline__ bool con_owns(const ConSeg& sg, int x) {
+    const unsigned u = ((unsigned)x * 2654435769u) >> 1;
+    return u >= sg.tb && u < sg.te;
 }
 
-// Work decomposition ("stream-K"): the (matrix z, tile pair) items, each nchunk k-chunks long and weighted by their
-// DMMA cost, are laid end to end and cut into one equal share per CTA (one CTA per SM).  A CTA therefore executes 1-3
-// segments = (z, pair, [c_begin, c_end)) and writes one partial tile per segment; k_contract_reduce adds an item's
-// partial tiles in a fixed order.  The schedule is built on the host (dftgrid_api.cu).  Chunk positions index the list
-// of non-zero chunks (chunk_ids).
-struct ConSeg {
-    int z, pair, c_begin, c_end;
-};
+// Number of chunk positions of [x0, x1) owned by the segment (warp-collective, same value in every lane).
+__device__ __forceinline__ int con_count_owned(const ConSeg& sg, int x0, int x1, int lane) {
+    int cnt = 0;
+    for (int base = x0; base < x1; base += 32) {
+        const int x = base + lane;
+        cnt += __popc(__ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x)));
+    }
+    return cnt;
+}
 
 constexpr int kConTmaThreads = kDenseThreads + 32;
 constexpr size_t kConTmaSmemBytes = (size_t)kStages * kConStageDoubles * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
@@ -404,12 +398,154 @@ __device__ __forceinline__ void con_run_segment(const double* sm, unsigned long 
     }
 }
 
+// Accumulator tile layouts of the four segment kinds: how the DMMA stage, the store to and the reload from the
+// segment's partial tile address the 32 accumulator pairs.
+struct ConModeFull {
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 16>(st, acc, warp, lane); }
+    template <bool LOAD>
+    static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
+        const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 16; nt++) {
+                double2* p = reinterpret_cast<double2*>(out + (warp * 16 + mt * 8 + g) * kTileN + nt * 8 + q * 2);
+                if (LOAD) {
+                    const double2 v = *p;
+                    acc[mt * 16 + nt][0] = v.x;
+                    acc[mt * 16 + nt][1] = v.y;
+                } else {
+                    *p = make_double2(acc[mt * 16 + nt][0], acc[mt * 16 + nt][1]);
+                }
+            }
+    }
+};
+struct ConModeNarrow {
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 8>(st, acc, warp, lane); }
+    template <bool LOAD>
+    static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
+        const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                double2* p = reinterpret_cast<double2*>(out + (warp * 16 + mt * 8 + g) * kTileN + nt * 8 + q * 2);
+                if (LOAD) {
+                    const double2 v = *p;
+                    acc[mt * 8 + nt][0] = v.x;
+                    acc[mt * 8 + nt][1] = v.y;
+                } else {
+                    *p = make_double2(acc[mt * 8 + nt][0], acc[mt * 8 + nt][1]);
+                }
+            }
+    }
+};
+struct ConModeDiagEdge {
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage_diag_edge(st, acc, warp, lane); }
+    template <bool LOAD>
+    static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
+        const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            double2* p = reinterpret_cast<double2*>(out + (warp * 8 + g) * kTileN + nt * 8 + q * 2);
+            if (LOAD) {
+                const double2 v = *p;
+                acc[nt][0] = v.x;
+                acc[nt][1] = v.y;
+            } else {
+                *p = make_double2(acc[nt][0], acc[nt][1]);
+            }
+        }
+    }
+};
+template <int W>
+struct ConModeTri {
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int, int lane) { con_mma_stage_tri<W>(st, acc, lane); }
+    template <bool LOAD>
+    static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int, int lane) {
+        const int g = lane >> 2, q = lane & 3;
+        constexpr int NB = 16 - W;
+#pragma unroll
+        for (int c = 0; c < NB; c++) {
+            double2* p = reinterpret_cast<double2*>(out + (W * 8 + g) * kTileN + (W + c) * 8 + q * 2);
+            if (LOAD) {
+                const double2 v = *p;
+                acc[c][0] = v.x;
+                acc[c][1] = v.y;
+            } else {
+                *p = make_double2(acc[c][0], acc[c][1]);
+            }
+        }
+#pragma unroll
+        for (int c = 15 - W; c < 16; c++) {
+            double2* p = reinterpret_cast<double2*>(out + ((15 - W) * 8 + g) * kTileN + c * 8 + q * 2);
+            if (LOAD) {
+                const double2 v = *p;
+                acc[NB + c - (15 - W)][0] = v.x;
+                acc[NB + c - (15 - W)][1] = v.y;
+            } else {
+                *p = make_double2(acc[NB + c - (15 - W)][0], acc[NB + c - (15 - W)][1]);
+            }
+        }
+    }
+};
+
+// Blocks [b_begin, b_end) of one segment for one DMMA warp: accumulators start from zero (`fresh`) or from the
+// segment's partial tile, and are written back to it at the end.
+template <class Mode>
+__device__ __forceinline__ void con_segment_blocks_mode(const double* sm, unsigned long long* full, unsigned long long* empty, unsigned& n, int warp,
+                                                        int lane, const ConSeg& sg, double* out, int nchunk, int bc, int b_begin, int b_end,
+                                                        bool fresh) {
+    double acc[32][2];
+    if (fresh) {
+#pragma unroll
+        for (int t = 0; t < 32; t++) acc[t][0] = acc[t][1] = 0.0;
+    } else {
+        Mode::template io<true>(out, acc, warp, lane);
+    }
+    {
+        const int x0 = min(b_begin * bc, nchunk), x1 = min(b_end * bc, nchunk);
+        con_run_segment(sm, full, empty, con_count_owned(sg, x0, x1, lane), n, lane, [&](const double* st) { Mode::mma(st, acc, warp, lane); });
+    }
+    Mode::template io<false>(out, acc, warp, lane);
+}
+
+__device__ __forceinline__ void con_segment_blocks(const double* sm, unsigned long long* full, unsigned long long* empty, unsigned& n, int warp, int lane,
+                                                   const ConSeg sg, const int* __restrict__ pair_ij, double* out, int nbp, int nchunk, int bc,
+                                                   int b_begin, int b_end, bool fresh) {
+    const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
+    const bool diag = ti == tj;
+    const bool narrow = min(kTileN, nbp - tj * kTileN) <= 64;
+#define DFG_SEG_ARGS sm, full, empty, n, warp, lane, sg, out, nchunk, bc, b_begin, b_end, fresh
+    if (!diag) {
+        if (narrow)
+            con_segment_blocks_mode<ConModeNarrow>(DFG_SEG_ARGS);
+        else
+            con_segment_blocks_mode<ConModeFull>(DFG_SEG_ARGS);
+    } else if (narrow) {
+        con_segment_blocks_mode<ConModeDiagEdge>(DFG_SEG_ARGS);
+    } else {
+        switch (warp) {
+            case 0: con_segment_blocks_mode<ConModeTri<0>>(DFG_SEG_ARGS); break;
+            case 1: con_segment_blocks_mode<ConModeTri<1>>(DFG_SEG_ARGS); break;
+            case 2: con_segment_blocks_mode<ConModeTri<2>>(DFG_SEG_ARGS); break;
+            case 3: con_segment_blocks_mode<ConModeTri<3>>(DFG_SEG_ARGS); break;
+            case 4: con_segment_blocks_mode<ConModeTri<4>>(DFG_SEG_ARGS); break;
+            case 5: con_segment_blocks_mode<ConModeTri<5>>(DFG_SEG_ARGS); break;
+            case 6: con_segment_blocks_mode<ConModeTri<6>>(DFG_SEG_ARGS); break;
+            default: con_segment_blocks_mode<ConModeTri<7>>(DFG_SEG_ARGS); break;
+        }
+    }
+#undef DFG_SEG_ARGS
+}
+
 // grid = number of CTAs in the schedule.  d0/d1: per-point weights of matrix 0/1 (zero-padded past the shard).
 // phi must be readable for whole 32-row chunks (rows past nloc are zero).  partial: [nseg][128*128].
+// nchunk = number of non-zero chunks (length of chunk_ids), bc = chunks per L2 block.
 __global__ void __launch_bounds__(kConTmaThreads, 1)
 k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, const double* __restrict__ d1, const int* __restrict__ chunk_ids,
                const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs, const int* __restrict__ cta_seg_off,
-               double* __restrict__ partial, int nbp) {
+               double* __restrict__ partial, int nbp, int nchunk, int bc) {
     extern __shared__ __align__(128) double sm[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)kStages * kConStageDoubles);
     unsigned long long* empty = full + kStages;
@@ -423,72 +559,61 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
     }
     __syncthreads();
     const int s_begin = cta_seg_off[blockIdx.x], s_end = cta_seg_off[blockIdx.x + 1];
-    unsigned n = 0;  // running stage counter, continues across segments
+    const int nblock = bc > 0 ? (nchunk + bc - 1) / bc : 0;
+    unsigned n = 0;  // running stage counter, continues across segments and blocks
     if (warp == 8) {
-        // ===== producer warp: one 1 KB Phi row (per operand) per lane and stage =====
-        for (int sidx = s_begin; sidx < s_end; sidx++) {
-            const ConSeg sg = segs[sidx];
-            const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
-            const int ci = ti * kTileM, cj = tj * kTileN;
-            const bool diag = ti == tj;
-            const double* d = sg.z == 0 ? d0 : d1;
-            const unsigned wi = (unsigned)min(kTileM, nbp - ci) * 8u, wj = (unsigned)min(kTileN, nbp - cj) * 8u;  // valid row bytes
-            const unsigned bytes = kTileK * (wi + (diag ? 0u : wj)) + kTileK * 8u;
-            for (int c = sg.c_begin; c < sg.c_end; c++, n++) {
-                const unsigned stage = n % kStages, round = n / kStages;
-                double* st = sm + (size_t)stage * kConStageDoubles;
-                const size_t row0 = (size_t)chunk_ids[c] * kTileK;
-                mbar_wait(empty + stage, (round & 1u) ^ 1u);
-                if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes);
-                __syncwarp();
-                const double* row = phi + (row0 + lane) * (size_t)nbp;
-                bulk_copy_g2s(st + lane * kLdN, row + ci, wi, full + stage);
-                if (!diag) bulk_copy_g2s(st + kTileK * kLdN + lane * kLdN, row + cj, wj, full + stage);
-                if (lane == 0) bulk_copy_g2s(st + 2 * kTileK * kLdN, d + row0, kTileK * 8u, full + stage);
+        // ===== producer warp: one 1 KB Phi row (per operand) per lane and stage; block-major, like the consumers =====
+        for (int b = 0; b < nblock; b++) {
+            for (int sidx = s_begin; sidx < s_end; sidx++) {
+                const ConSeg sg = segs[sidx];
+                const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
+                const int ci = ti * kTileM, cj = tj * kTileN;
+                const bool diag = ti == tj;
+                const double* d = sg.z == 0 ? d0 : d1;
+                const unsigned wi = (unsigned)min(kTileM, nbp - ci) * 8u, wj = (unsigned)min(kTileN, nbp - cj) * 8u;  // valid row bytes
+                const unsigned bytes = kTileK * (wi + (diag ? 0u : wj)) + kTileK * 8u;
+                const int x0 = min(b * bc, nchunk), x1 = min((b + 1) * bc, nchunk);
+                for (int base = x0; base < x1; base += 32) {
+                    const int x = base + lane;
+                    unsigned mask = __ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x));
+                    const int my_chunk = x < x1 ? chunk_ids[x] : 0;
+                    while (mask) {
+                        const int src = __ffs(mask) - 1;
+                        mask &= mask - 1u;
+                        const size_t row0 = (size_t)__shfl_sync(0xffffffffu, my_chunk, src) * kTileK;
+                        const unsigned stage = n % kStages, round = n / kStages;
+                        double* st = sm + (size_t)stage * kConStageDoubles;
+                        mbar_wait(empty + stage, (round & 1u) ^ 1u);
+                        if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes);
+                        __syncwarp();
+                        const double* row = phi + (row0 + lane) * (size_t)nbp;
+                        bulk_copy_g2s(st + lane * kLdN, row + ci, wi, full + stage);
+                        if (!diag) bulk_copy_g2s(st + kTileK * kLdN + lane * kLdN, row + cj, wj, full + stage);
+                        if (lane == 0) bulk_copy_g2s(st + 2 * kTileK * kLdN, d + row0, kTileK * 8u, full + stage);
+                        n++;
+                    }
+                }
             }
         }
         return;
     }
     // ===== DMMA warps =====
-    for (int sidx = s_begin; sidx < s_end; sidx++) {
-        const ConSeg sg = segs[sidx];
-        const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
-        const bool diag = ti == tj;
-        const bool narrow = min(kTileN, nbp - tj * kTileN) <= 64;
-        const int nch = sg.c_end - sg.c_begin;
-        double* out = partial + (size_t)sidx * (size_t)(kTileM * kTileN);
-        double acc[32][2];
-#pragma unroll
-        for (int t = 0; t < 32; t++) acc[t][0] = acc[t][1] = 0.0;
-        if (!diag) {
-            if (narrow) {
-                con_run_segment(sm, full, empty, nch, n, lane, [&](const double* st) { con_mma_stage<2, 8>(st, acc, warp, lane); });
-                con_store<2, 8>(out, acc, warp, lane);
-            } else {
-                con_run_segment(sm, full, empty, nch, n, lane, [&](const double* st) { con_mma_stage<2, 16>(st, acc, warp, lane); });
-                con_store<2, 16>(out, acc, warp, lane);
-            }
-        } else if (narrow) {
-            con_run_segment(sm, full, empty, nch, n, lane, [&](const double* st) { con_mma_stage_diag_edge(st, acc, warp, lane); });
-            con_store_diag_edge(out, acc, warp, lane);
-        } else {
-#define DFG_TRI_CASE(W)                                                                                                  \
-    case W:                                                                                                              \
-        con_run_segment(sm, full, empty, nch, n, lane, [&](const double* st) { con_mma_stage_tri<W>(st, acc, lane); }); \
-        con_store_tri<W>(out, acc, lane);                                                                                \
-        break;
-            switch (warp) {
-                DFG_TRI_CASE(0)
-                DFG_TRI_CASE(1)
-                DFG_TRI_CASE(2)
-                DFG_TRI_CASE(3)
-                DFG_TRI_CASE(4)
-                DFG_TRI_CASE(5)
-                DFG_TRI_CASE(6)
-                DFG_TRI_CASE(7)
-            }
-#undef DFG_TRI_CASE
-        }
+    // A CTA with a single segment keeps its accumulators in registers while the blocks go by.  A CTA whose share crosses
+    // an item boundary (2-3 segments) visits its segments in turn inside every block and parks the accumulators of the
+    // inactive ones in their partial tiles (L2-resident) in between.
+    const int nseg = s_end - s_begin;
+    if (nseg == 1) {
+        con_segment_blocks(sm, full, empty, n, warp, lane, segs[s_begin], pair_ij, partial + (size_t)s_begin * (size_t)(kTileM * kTileN), nbp, nchunk, bc,
+                           0, nblock, true);
+    } else {
+        for (int b = 0; b < nblock; b++)
+            for (int sidx = s_begin; sidx < s_end; sidx++)
+                con_segment_blocks(sm, full, empty, n, warp, lane, segs[sidx], pair_ij, partial + (size_t)sidx * (size_t)(kTileM * kTileN), nbp, nchunk,
+                                   bc, b, b + 1, b == 0);
+        if (nblock == 0)  // empty shard: the reduction still reads every segment's tile
+            for (int sidx = s_begin; sidx < s_end; sidx++)
+                con_segment_blocks(sm, full, empty, n, warp, lane, segs[sidx], pair_ij, partial + (size_t)sidx * (size_t)(kTileM * kTileN), nbp, nchunk,
+                                   bc, 0, 0, true);
     }
 }
 
