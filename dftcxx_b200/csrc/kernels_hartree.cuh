@@ -272,10 +272,8 @@ k_interp(GridShape g, const double* __restrict__ atom_xyz, const double* __restr
     extern __shared__ double sm[];
     const int N = g.nrad, L = g.lmax;
     double* xsh = sm;            // [N]
-    double* presh = sm + N;      // [(L+1)^2]
-    double* rj = presh + (L + 1) * (L + 1);  // [2L+2] reciprocals 1/(j-m)
+    double* rj = sm + N;         // [2L+2] reciprocals 1/(j-m)
     for (int i = threadIdx.x; i < N; i += blockDim.x) xsh[i] = xs[i];
-    for (int i = threadIdx.x; i < (L + 1) * (L + 1); i += blockDim.x) presh[i] = pre[i];
     for (int i = threadIdx.x; i < 2 * L + 2; i += blockDim.x) rj[i] = i > 0 ? 1.0 / (double)i : 0.0;
     __syncthreads();
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,9 +384,7 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
     // Warps spanning more than two intervals fall back to per-lane global loads through the same (generic) pointer.
     double4* rows = reinterpret_cast<double4*>(sm) + (size_t)(threadIdx.x >> 5) * 2 * NLM;  // [4 warps][2][NLM]
     double* xsh = sm + (size_t)4 * 2 * NLM * 4;                                              // [N]
-    double* presh = xsh + N;                                                                  // [(L+1)^2]
     for (int i = threadIdx.x; i < N; i += blockDim.x) xsh[i] = xs[i];
-    for (int i = threadIdx.x; i < (L + 1) * (L + 1); i += blockDim.x) presh[i] = pre[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long pr = (long)blockIdx.x * blockDim.x + threadIdx.x;
