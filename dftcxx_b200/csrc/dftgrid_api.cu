@@ -683,9 +683,12 @@ void run_potential(dftgrid* h) {
     const long nsys = (long)g.natoms * g.nlm;
     double* rho_lm = h->d_shell2.p + (size_t)nshell * 2;
     record(h, 9);
-    k_poisson<<<(unsigned)((nsys + 63) / 64), 64, 0, st>>>(g, g.nrad + 2, h->d_lu.p, h->d_perm.p, h->d_lo.p, h->d_hi.p, h->d_rtab.p,
-                                                          rho_lm, h->d_qatom.p, h->d_work.p, h->d_U_lm.p);
-    k_spline<<<(unsigned)((nsys + 63) / 64), 64, 0, st>>>(g, h->spline, h->d_U_lm.p, h->d_pre.p, h->d_work.p, h->d_coef.p);
+    // per-thread scratch vectors in shared memory when they fit the default 48 KB (radial grids up to ~90 nodes)
+    const size_t sm_poisson = (size_t)(g.nrad + 2) * 64 * sizeof(double), sm_spline = (size_t)2 * g.nrad * 64 * sizeof(double);
+    const bool smp = sm_poisson <= 48 * 1024, sms = sm_spline <= 48 * 1024;
+    k_poisson<<<(unsigned)((nsys + 63) / 64), 64, smp ? sm_poisson : 0, st>>>(g, g.nrad + 2, h->d_lu.p, h->d_perm.p, h->d_lo.p, h->d_hi.p,
+                                                                              h->d_rtab.p, rho_lm, h->d_qatom.p, h->d_work.p, h->d_U_lm.p, smp);
+    k_spline<<<(unsigned)((nsys + 63) / 64), 64, sms ? sm_spline : 0, st>>>(g, h->spline, h->d_U_lm.p, h->d_pre.p, h->d_work.p, h->d_coef.p, sms);
     h->launches += 2;
     if (g.nloc > 0) {
         k_v_own<<<(unsigned)g.nshell_loc, 128, g.nlm * sizeof(double), st>>>(g, h->d_rtab.p, h->d_leb.p, h->d_Yt.p, h->d_U_lm.p, h->d_Vown.p);

@@ -109,6 +109,7 @@ k_becke(GridShape g, const double* __restrict__ atom_xyz, const double* __restri
 #endif
 constexpr int kPhiPts = 128;
 constexpr int kPhiCols = 32;    // one 256-byte row segment per point and pass
+constexpr int kPhiBatch = 3;    // primitives of a shell fetched together (6-31G shells have 1, 3 or 6)
 constexpr int kPhiMaxExp = 24;  // distinct exponents on one centre (STO-6G third row needs 18)
 
 enum { kShellGeneric = 0, kShellS = 1, kShellP = 2, kShellD = 3 };
@@ -156,9 +157,22 @@ k_phi(long nloc, PhiBasis B, const double* __restrict__ px, const double* __rest
 #pragma unroll 4
         for (int c = 0; c < kPhiCols; c++) trow[c] = 0.0;  // pad columns and columns of shells outside this pass
         const int s0 = __ldg(B.pass_shell_rng + 2 * pass), s1 = __ldg(B.pass_shell_rng + 2 * pass + 1);
+        // the shell and primitive records are the same for every thread (warp-uniform loads); what costs is their
+        // latency in front of each dependent step, so the next shell's record is fetched one iteration ahead and a
+        // shell's primitives are fetched together before any of them is used
+        int4 sa_n = make_int4(0, 0, 0, 0);
+        int2 sb_n = make_int2(0, 0);
+        if (s0 < s1) {
+            sa_n = __ldg(reinterpret_cast<const int4*>(B.shells + s0));
+            sb_n = __ldg(reinterpret_cast<const int2*>(B.shells + s0) + 2);
+        }
         for (int si = s0; si < s1; si++) {
-            const int4 sa = __ldg(reinterpret_cast<const int4*>(B.shells + si));      // type, col, centre, prim_off
-            const int2 sb = __ldg(reinterpret_cast<const int2*>(B.shells + si) + 2);  // nprim, ncol
+            const int4 sa = sa_n;  // type, col, centre, prim_off
+            const int2 sb = sb_n;  // nprim, ncol
+            if (si + 1 < s1) {
+                sa_n = __ldg(reinterpret_cast<const int4*>(B.shells + si + 1));
+                sb_n = __ldg(reinterpret_cast<const int2*>(B.shells + si + 1) + 2);
+            }
             if (sa.z != cur) {
                 cur = sa.z;
                 dx = __dsub_rn(x, __ldg(B.centre_xyz + 3 * cur));
@@ -184,21 +198,38 @@ k_phi(long nloc, PhiBasis B, const double* __restrict__ px, const double* __rest
             const int rel = sa.y - c0;  // first column of the shell relative to this pass (may be negative)
             if (sa.x == kShellS) {
                 double v = 0.0;
-                for (int k = 0; k < sb.x; k++) {
-                    const double2 cn = __ldg(reinterpret_cast<const double2*>(pr + k));
-                    const int slot = __ldg(reinterpret_cast<const int*>(pr + k) + 6);
-                    v = __dadd_rn(v, __dmul_rn(cn.x, __dmul_rn(cn.y, exl[(size_t)slot * kPhiPts])));
+                for (int k0 = 0; k0 < sb.x; k0 += kPhiBatch) {
+                    double2 cn[kPhiBatch];
+                    double e[kPhiBatch];
+#pragma unroll
+                    for (int u = 0; u < kPhiBatch; u++)
+                        if (k0 + u < sb.x) cn[u] = __ldg(reinterpret_cast<const double2*>(pr + k0 + u));
+#pragma unroll
+                    for (int u = 0; u < kPhiBatch; u++)
+                        if (k0 + u < sb.x) e[u] = exl[(size_t)__ldg(reinterpret_cast<const int*>(pr + k0 + u) + 6) * kPhiPts];
+#pragma unroll
+                    for (int u = 0; u < kPhiBatch; u++)
+                        if (k0 + u < sb.x) v = __dadd_rn(v, __dmul_rn(cn[u].x, __dmul_rn(cn[u].y, e[u])));
                 }
                 trow[rel] = v;
             } else if (sa.x == kShellP) {
                 double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-                for (int k = 0; k < sb.x; k++) {
-                    const double2 cn = __ldg(reinterpret_cast<const double2*>(pr + k));
-                    const int slot = __ldg(reinterpret_cast<const int*>(pr + k) + 6);
-                    const double e = exl[(size_t)slot * kPhiPts];
-                    v0 = __dadd_rn(v0, __dmul_rn(cn.x, __dmul_rn(__dmul_rn(cn.y, dx), e)));
-                    v1 = __dadd_rn(v1, __dmul_rn(cn.x, __dmul_rn(__dmul_rn(cn.y, dy), e)));
-                    v2 = __dadd_rn(v2, __dmul_rn(cn.x, __dmul_rn(__dmul_rn(cn.y, dz), e)));
+                for (int k0 = 0; k0 < sb.x; k0 += kPhiBatch) {
+                    double2 cn[kPhiBatch];
+                    double e[kPhiBatch];
+#pragma unroll
+                    for (int u = 0; u < kPhiBatch; u++)
+                        if (k0 + u < sb.x) cn[u] = __ldg(reinterpret_cast<const double2*>(pr + k0 + u));
+#pragma unroll
+                    for (int u = 0; u < kPhiBatch; u++)
+                        if (k0 + u < sb.x) e[u] = exl[(size_t)__ldg(reinterpret_cast<const int*>(pr + k0 + u) + 6) * kPhiPts];
+#pragma unroll
+                    for (int u = 0; u < kPhiBatch; u++)
+                        if (k0 + u < sb.x) {
+                            v0 = __dadd_rn(v0, __dmul_rn(cn[u].x, __dmul_rn(__dmul_rn(cn[u].y, dx), e[u])));
+                            v1 = __dadd_rn(v1, __dmul_rn(cn[u].x, __dmul_rn(__dmul_rn(cn[u].y, dy), e[u])));
+                            v2 = __dadd_rn(v2, __dmul_rn(cn[u].x, __dmul_rn(__dmul_rn(cn[u].y, dz), e[u])));
+                        }
                 }
                 if (rel >= 0 && rel < kPhiCols) trow[rel] = v0;
                 if (rel + 1 >= 0 && rel + 1 < kPhiCols) trow[rel + 1] = v1;

@@ -124,7 +124,7 @@ __global__ void k_rho_lm(GridShape g, const double* __restrict__ rho, const doub
 __global__ void k_poisson(GridShape g, int n /*N+2*/, const double* __restrict__ lu, const int* __restrict__ perm,
                           const int* __restrict__ lo, const int* __restrict__ hi, const double* __restrict__ r_tab,
                           const double* __restrict__ rho_lm, const double* __restrict__ q_atom,
-                          double* __restrict__ work, double* __restrict__ U_lm /*[natoms*nrad][nlm]*/) {
+                          double* __restrict__ work, double* __restrict__ U_lm /*[natoms*nrad][nlm]*/, bool use_smem) {
     const long nsys = (long)g.natoms * g.nlm;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsys) return;
@@ -142,18 +142,23 @@ __global__ void k_poisson(GridShape g, int n /*N+2*/, const double* __restrict__
         if (i == N + 1) return 0.0;
         return -4.0 * 3.14159265358979323846 * r_tab[i - 1] * rho_lm[((long)atom * g.nrad + (i - 1)) * g.nlm + lm];
     };
-    double* x = work + t;  // stride nsys
+    // scratch vector of this system: shared memory [n][blockDim] when the launch provides it (small radial grids: the
+    // substitution is a chain of dependent loads, ~30 clocks each from shared memory against a global round trip),
+    // else the global work array [n][nsys]
+    extern __shared__ double sx[];
+    double* x = use_smem ? sx + threadIdx.x : work + t;
+    const size_t xs_ = use_smem ? (size_t)blockDim.x : (size_t)nsys;
     for (int i = 0; i < n; i++) {  // L y = P g
         double acc = rhs(pr[i]);
-        for (int j = lor[i]; j < i; j++) acc -= M[(size_t)i * n + j] * x[(size_t)j * nsys];
-        x[(size_t)i * nsys] = acc;
+        for (int j = lor[i]; j < i; j++) acc -= M[(size_t)i * n + j] * x[(size_t)j * xs_];
+        x[(size_t)i * xs_] = acc;
     }
     for (int i = n - 1; i >= 0; i--) {  // U x = y
-        double acc = x[(size_t)i * nsys];
-        for (int j = hir[i]; j > i; j--) acc -= M[(size_t)i * n + j] * x[(size_t)j * nsys];
-        x[(size_t)i * nsys] = acc / M[(size_t)i * n + i];
+        double acc = x[(size_t)i * xs_];
+        for (int j = hir[i]; j > i; j--) acc -= M[(size_t)i * n + j] * x[(size_t)j * xs_];
+        x[(size_t)i * xs_] = acc / M[(size_t)i * n + i];
     }
-    for (int i = 1; i < N + 1; i++) U_lm[((long)atom * g.nrad + (i - 1)) * g.nlm + lm] = x[(size_t)i * nsys];
+    for (int i = 1; i < N + 1; i++) U_lm[((long)atom * g.nrad + (i - 1)) * g.nlm + lm] = x[(size_t)i * xs_];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -181,7 +186,7 @@ struct SplineDev {
 };
 
 __global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_lm, const double* __restrict__ pre /*[(lmax+1)^2]*/,
-                         double* __restrict__ work /*[2][N][nsys]*/, double* __restrict__ coef) {
+                         double* __restrict__ work /*[2][N][nsys]*/, double* __restrict__ coef, bool use_smem) {
     const long nsys = (long)g.natoms * g.nlm;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nsys) return;
@@ -198,8 +203,11 @@ __global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_
         const int m = lm - l * l - l;
         pf = pre[l * (g.lmax + 1) + (m < 0 ? -m : m)];
     }
-    double* Y = work + t;                        // stride nsys
-    double* D = work + (size_t)N * nsys + t;     // stride nsys
+    // scratch [2][N] per system: shared memory [2N][blockDim] when provided, else the global work array (stride nsys)
+    extern __shared__ double sx[];
+    double* Y = use_smem ? sx + threadIdx.x : work + t;
+    double* D = use_smem ? sx + (size_t)N * blockDim.x + threadIdx.x : work + (size_t)N * nsys + t;
+    const size_t ws_ = use_smem ? (size_t)blockDim.x : (size_t)nsys;
     // right-hand sides (src/cspline.cpp:81-109)
     {
         const double r0 = (y(1) - y(0)) / S.h[0], r1 = (y(2) - y(1)) / S.h[1];
@@ -209,19 +217,19 @@ __global__ void k_spline(GridShape g, SplineDev S, const double* __restrict__ U_
     for (int i = 1; i < N - 1; i++) {
         r0 = (y(i) - y(i - 1)) / S.h[i - 1];
         r1 = (y(i + 1) - y(i)) / S.h[i];
-        Y[(size_t)i * nsys] = 3 * (r0 * S.h[i] + r1 * S.h[i - 1]);
+        Y[(size_t)i * ws_] = 3 * (r0 * S.h[i] + r1 * S.h[i - 1]);
     }
-    Y[(size_t)(N - 1) * nsys] = r0 * S.lh1 * S.lh1 + r1 * S.lw1;
+    Y[(size_t)(N - 1) * ws_] = r0 * S.lh1 * S.lh1 + r1 * S.lw1;
     // forward sweep and back substitution (src/cspline.cpp:111-127)
     Y[0] = Y[0] / S.den[0];
-    for (int i = 1; i < N; i++) Y[(size_t)i * nsys] = (Y[(size_t)i * nsys] - S.A[i] * Y[(size_t)(i - 1) * nsys]) / S.den[i];
-    D[(size_t)(N - 1) * nsys] = Y[(size_t)(N - 1) * nsys];
-    for (int i = N - 1; i > 0; i--) D[(size_t)(i - 1) * nsys] = Y[(size_t)(i - 1) * nsys] - S.Cp[i - 1] * D[(size_t)i * nsys];
+    for (int i = 1; i < N; i++) Y[(size_t)i * ws_] = (Y[(size_t)i * ws_] - S.A[i] * Y[(size_t)(i - 1) * ws_]) / S.den[i];
+    D[(size_t)(N - 1) * ws_] = Y[(size_t)(N - 1) * ws_];
+    for (int i = N - 1; i > 0; i--) D[(size_t)(i - 1) * ws_] = Y[(size_t)(i - 1) * ws_] - S.Cp[i - 1] * D[(size_t)i * ws_];
     // polynomial coefficients (src/cspline.cpp:130-139)
     for (int i = 0; i < N - 1; i++) {
         const double dx = S.rh[i];
         const double dy = (y(i + 1) - y(i)) * dx;
-        const double Di = D[(size_t)i * nsys], Dn = D[(size_t)(i + 1) * nsys];
+        const double Di = D[(size_t)i * ws_], Dn = D[(size_t)(i + 1) * ws_];
         double4 c;
         c.x = pf * y(i);
         c.y = pf * Di;
