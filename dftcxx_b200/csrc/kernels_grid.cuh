@@ -104,9 +104,6 @@ k_becke(GridShape g, const double* __restrict__ atom_xyz, const double* __restri
 // Multiplying by pow(x,0) = 1.0 is exact, so the generic path multiplies by a selected factor instead of branching.
 // A [kPhiPts x kPhiCols] tile is staged in shared memory so that every Phi row is written with full 256-byte
 // coalesced segments; pad columns [nbf, nbp) are written as zeros.
-#ifndef DFG_PHI_BRANCHLESS_EXP
-#define DFG_PHI_BRANCHLESS_EXP 0
-#endif
 constexpr int kPhiPts = 128;
 constexpr int kPhiCols = 32;    // one 256-byte row segment per point and pass
 constexpr int kPhiBatch = 3;    // primitives of a shell fetched together (6-31G shells have 1, 3 or 6)
@@ -180,19 +177,26 @@ k_phi(long nloc, PhiBasis B, const double* __restrict__ px, const double* __rest
                 dz = __dsub_rn(z, __ldg(B.centre_xyz + 3 * cur + 2));
                 const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                 const int e0 = __ldg(B.centre_exp_off + cur), e1 = __ldg(B.centre_exp_off + cur + 1);
-#if DFG_PHI_BRANCHLESS_EXP
-#pragma unroll 2
-                for (int u = e0; u < e1; u++) {
-                    const double arg = __dmul_rn(__ldg(B.exp_alpha + u), r2);
-                    const double ev = exp(-fmin(arg, 746.0));
-                    ex[(size_t)(u - e0) * kPhiPts + tid] = arg > 746.0 ? 0.0 : ev;
+                // exponentials of this centre, four at a time: the four evaluations are independent instruction chains
+                // (one exp() is ~25 dependent FP64 operations), and a group is skipped altogether when no lane of the warp
+                // needs it (alpha r^2 > 746 underflows to exactly +0, the common case for tight exponents far away)
+                for (int u = e0; u < e1; u += 4) {
+                    double arg[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) arg[t] = u + t < e1 ? __dmul_rn(__ldg(B.exp_alpha + u + t), r2) : 1e300;
+                    const bool need = arg[0] <= 746.0 || arg[1] <= 746.0 || arg[2] <= 746.0 || arg[3] <= 746.0;
+                    double ev[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const double e_ = exp(-fmin(arg[t], 746.0));
+                            ev[t] = arg[t] > 746.0 ? 0.0 : e_;
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (u + t < e1) ex[(size_t)(u + t - e0) * kPhiPts + tid] = ev[t];
                 }
-#else
-                for (int u = e0; u < e1; u++) {
-                    const double arg = __dmul_rn(__ldg(B.exp_alpha + u), r2);
-                    ex[(size_t)(u - e0) * kPhiPts + tid] = arg > 746.0 ? 0.0 : exp(-arg);
-                }
-#endif
             }
             const PhiPrim* pr = B.prims + sa.w;
             const int rel = sa.y - c0;  // first column of the shell relative to this pass (may be negative)
