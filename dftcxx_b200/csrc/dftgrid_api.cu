@@ -612,7 +612,12 @@ void do_build(dftgrid* h) {
         h->d_pass_rng.upload(pass_rng, st);
         PhiBasis B{h->nbf, h->nbp, (int)shells.size(), h->d_shells.p, h->d_prims.p, h->d_center_exp_off.p, h->d_exp_alpha.p, h->d_center_xyz.p,
                    h->d_pass_rng.p};
-        const size_t smem = ((size_t)kPhiPts * (kPhiCols + 1) + (size_t)kPhiMaxExp * kPhiPts) * sizeof(double);
+        // the exponential table is sized for the molecule's largest centre (rounded up to the group of four), not for
+        // kPhiMaxExp: with 6-31G (10 exponents on O) four CTAs fit an SM instead of three
+        int max_exp = 1;
+        for (size_t c = 0; c + 1 < h->center_exp_off.size(); c++) max_exp = std::max(max_exp, h->center_exp_off[c + 1] - h->center_exp_off[c]);
+        max_exp = std::min(kPhiMaxExp, (max_exp + 3) / 4 * 4);
+        const size_t smem = ((size_t)kPhiPts * (kPhiCols + 1) + (size_t)max_exp * kPhiPts) * sizeof(double);
         k_phi<<<(unsigned)((g.nloc + kPhiPts - 1) / kPhiPts), kPhiPts, smem, st>>>(g.nloc, B, h->d_x.p, h->d_y.p, h->d_z.p, h->d_phi.p);
         h->launches++;
     }

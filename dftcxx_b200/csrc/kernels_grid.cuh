@@ -133,12 +133,12 @@ struct PhiBasis {
     const int* pass_shell_rng;  // [npass][2]: first / one-past-last shell intersecting column pass c (kPhiCols columns each)
 };
 
-__global__ void __launch_bounds__(kPhiPts, 3)
+__global__ void __launch_bounds__(kPhiPts, 4)
 k_phi(long nloc, PhiBasis B, const double* __restrict__ px, const double* __restrict__ py,
       const double* __restrict__ pz, double* __restrict__ phi) {
     extern __shared__ double sm[];
     double* tile = sm;                                   // [kPhiPts][kPhiCols+1]
-    double* ex = sm + (size_t)kPhiPts * (kPhiCols + 1);  // [kPhiMaxExp][kPhiPts]
+    double* ex = sm + (size_t)kPhiPts * (kPhiCols + 1);  // [largest centre's exponent count][kPhiPts]
     const int tid = threadIdx.x;
     const long p0 = (long)blockIdx.x * kPhiPts;
     const long p = p0 + tid;
