@@ -244,14 +244,16 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
     double W1 = 0.0;  // cost of all items for one chunk
     for (int it = 0; it < nitems; it++) {
         const int ti = pairs[2 * (it % h->npairs)], tj = pairs[2 * (it % h->npairs) + 1];
-        // relative cost of one k-chunk of this tile pair (full off-diagonal 128x128 tile = 20): a 64-wide edge tile
-        // issues half the DMMAs but pays the same loads (measured ~0.6); a diagonal tile issues 17 of 32 DMMAs per
-        // warp (8 of 32 on the edge)
+        // relative cost of one k-chunk of this tile pair (full off-diagonal 128x128 tile = 20), calibrated by sweeps at
+        // (H2O)64, (H2O)32 and C40H82: a 64-wide edge tile issues half the DMMAs but pays the same loads (10.5), a
+        // diagonal tile issues 17 of 32 DMMAs per warp (11.5), the 64-wide diagonal tile 8 of 32 (6.5; under-estimating
+        // it makes its CTA the straggler, 5 costs 14 %)
         const char* nc = std::getenv("DFTGRID_NARROW_COST");
         const char* dc = std::getenv("DFTGRID_DIAG_COST");
         const bool narrow = std::min(kTileN, h->nbp - tj * kTileN) <= 64;
-        const int c_narrow = nc ? std::atoi(nc) : 11, c_diag = dc ? std::atoi(dc) : 12;
-        cost[it] = ti == tj ? (narrow ? 8 : c_diag) : (narrow ? c_narrow : 20);
+        const char* ec = std::getenv("DFTGRID_EDGE_DIAG_COST");
+        const double c_narrow = nc ? std::atof(nc) : 10.5, c_diag = dc ? std::atof(dc) : 11.5, c_edge_diag = ec ? std::atof(ec) : 6.5;
+        cost[it] = ti == tj ? (narrow ? c_edge_diag : c_diag) : (narrow ? c_narrow : 20.0);
         W1 += cost[it];
     }
     // block length (the period at which a CTA with several segments alternates between them): ~120 MB of Phi rows.

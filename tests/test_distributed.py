@@ -25,7 +25,7 @@ def test_shards_tile_the_grid_gloo(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["benzene_p631_fine", "h2o_sto3g"])
+@pytest.mark.parametrize("name", ["benzene_p631_fine", "h2o_sto3g", "ethane_p631_fine"])
 def test_sharded_iteration_matches_golden_nccl(name):
     import torch
 
