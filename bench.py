@@ -350,6 +350,8 @@ def main():
                                                                                   if peer_path else "ncclAllReduce")),
                "phases_ms": {k: round(v, 4) for k, v in phases.items()},
                "grid_build": {"wall_s": round(build_wall, 3), "becke_ms": tb["becke"], "phi_ms": tb["phi"],
+                              "becke_cell_functions_per_s": g.nloc * mol.natoms * (mol.natoms - 1) / (tb["becke"] * 1e-3) * world
+                              if tb["becke"] > 0 else None,
                               "phi_gridpt_basis_evals_per_s": g.nloc * mol.nbf / (tb["phi"] * 1e-3) * world if tb["phi"] > 0 else None,
                               "phi_hbm_write_frac": (g.nloc * mol.nbf * 8 / (tb["phi"] * 1e-3) / 1e9) / peaks.get("hbm_gbs", 6650.0)
                               if tb["phi"] > 0 else None},
