@@ -101,6 +101,9 @@ struct dftgrid {
     // device: per iteration
     DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
     DevBuf<int> d_pairs, d_cta_off, d_item_off, d_chunk_ids;
+    DevBuf<double> d_rho_part;  // partial densities when a tile's slabs are split over several CTAs
+    int rho_split = 1;
+    size_t rho_part_stride = 0;
     int con_bc = 1;
     long n_active_chunks = 0;
     DevBuf<ConSeg> d_segs;
@@ -347,6 +350,20 @@ void build_active_lists(dftgrid* h, int nsm) {
     while (chunk_ids.size() % 4 != 0 || chunk_ids.empty()) chunk_ids.push_back(-1);  // k_rho_tma reads groups of four
     h->d_chunk_ids.upload(chunk_ids, st);
     CK(cudaStreamSynchronize(st));
+    {
+        // k_rho_tma work items: one CTA per 128-point tile when that gives many waves over the SMs; with few waves
+        // (sharded grids, small molecules) the tail wave costs up to 1/waves, so a tile's column slabs are dealt to 2 or 3 CTAs
+        const double waves = (double)((h->n_active_chunks + 3) / 4) / (double)nsm;
+        const int nslab = (h->nbp + kTileN - 1) / kTileN;
+        int split = waves >= 40.0 ? 1 : (waves >= 12.0 ? 2 : 3);  // measured at (H2O)64: 28 waves 11.07 -> 10.98 ms (2 CTAs), 3.5 waves 1.56 -> 1.46 ms (3 CTAs)
+        if (const char* e = std::getenv("DFTGRID_RHO_SPLIT")) split = std::atoi(e);  // developer A/B switch
+        h->rho_split = std::max(1, std::min(split, std::min(nslab, 3)));
+        h->rho_part_stride = (size_t)g.nloc + 64;
+        if (h->rho_split > 1) {
+            h->d_rho_part.alloc((size_t)h->rho_split * h->rho_part_stride);
+            h->d_rho_part.zero(st);  // skipped (all-zero) chunks are never written
+        }
+    }
     build_contract_schedule(h, h->n_active_chunks, nsm);
 }
 
@@ -515,8 +532,7 @@ void do_build(dftgrid* h) {
         // source-atom chunks of the interpolation kernel: enough CTAs for >= ~8 full waves (6 CTAs of 128 threads per SM)
         const long ctas = (g.nloc + 127) / 128, wave = 6L * nsm;
         long chunks = ctas > 0 ? (8 * wave + ctas - 1) / ctas : 1;
-        h->interp_chunks = (int)std::max<long>(1, std::min<long>(chunks, std::min<long>(g.natoms, 32)));
-        h->d_Vpart.alloc((size_t)h->interp_chunks * (nl + 64));
+        h->interp_chunks = (int)std::max<long>(1, std::min<long>(chunks, std::min<long>(g.natoms, 32)));  // point-parallel fallback only
     }
     if (!h->h_P) CK(cudaMallocHost(&h->h_P, sizeof(double) * std::max<size_t>(1, (size_t)h->nbf * h->nbf)));
     if (!h->h_res) CK(cudaMallocHost(&h->h_res, sizeof(double) * ((size_t)2 * h->nbf * h->nbf + 2)));
@@ -641,9 +657,17 @@ void run_density(dftgrid* h) {
     const long nshell = (long)g.natoms * g.nrad;
     record(h, 4);
     if (g.nloc > 0) {
-        if (h->n_active_chunks > 0)
-            k_rho_tma<<<(unsigned)((h->n_active_chunks + 3) / 4), kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_chunk_ids.p, h->d_rho.p,
-                                                                                                     g.nloc, h->nbp);
+        if (h->n_active_chunks > 0) {
+            const unsigned tiles = (unsigned)((h->n_active_chunks + 3) / 4);
+            if (h->rho_split == 1) {
+                k_rho_tma<<<tiles, kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_chunk_ids.p, h->d_rho.p, 0, g.nloc, h->nbp);
+            } else {
+                k_rho_tma<<<dim3(tiles, h->rho_split), kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_chunk_ids.p, h->d_rho_part.p,
+                                                                                          (long)h->rho_part_stride, g.nloc, h->nbp);
+                k_rho_combine<<<(unsigned)((g.nloc + 255) / 256), 256, 0, st>>>(h->d_rho_part.p, (long)h->rho_part_stride, h->rho_split, g.nloc, h->d_rho.p);
+                h->launches++;
+            }
+        }
         h->launches++;
     }
     record(h, 5);
@@ -733,6 +757,7 @@ void run_potential(dftgrid* h) {
         k_finish_binned<<<(unsigned)((g.nloc + 255) / 256), 256, 0, st>>>(g, h->d_slot_of.p, h->d_pair_out.p, h->d_Vown.p, h->d_w.p, h->d_V.p, h->d_dJ.p);
         h->launches++;
     } else if (g.nloc > 0) {
+        if (h->d_Vpart.n == 0) h->d_Vpart.alloc((size_t)h->interp_chunks * ((size_t)g.nloc + 64));
         const size_t smem_g = ((size_t)g.nrad + (size_t)(g.lmax + 1) * (g.lmax + 1) + 2 * g.lmax + 2) * sizeof(double);
         const size_t smem = smem_g + (size_t)4 * 2 * g.nlm * 4 * sizeof(double);  // + per-warp staging rows of the unrolled kernels
         const unsigned bx = (unsigned)((g.nloc + 127) / 128);
@@ -756,7 +781,6 @@ void run_potential(dftgrid* h) {
 // [XC | J] = Phi^T diag(d) Phi, results laid out as res = [J (nb^2) | XC (nb^2) | exc | nel]
 void run_contract(dftgrid* h) {
     cudaStream_t st = h->stream;
-    const GridShape& g = h->g;
     const size_t nb2 = (size_t)h->nbf * h->nbf;
     record(h, 12);
     k_contract_tma<<<h->con_ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p, h->d_pairs.p,
@@ -778,7 +802,7 @@ void run_contract(dftgrid* h) {
     if (h->peer_ready) {
         const size_t n = 2 * nb2;
         const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 296);
-        k_peer_sum<<<blocks, 256, 0, st>>>(h->peers, h->peer_epoch, n, h->d_res.p);
+        k_peer_sum<<<blocks, 256, 0, st>>>(h->peers, h->peer_epoch, h->nbf, 2, h->d_res.p);
         h->launches++;
     } else {
         allreduce(h, h->d_res.p, 2 * nb2);

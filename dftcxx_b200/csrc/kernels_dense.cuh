@@ -131,7 +131,7 @@ __device__ __forceinline__ void rho_mma_stage(const double* st, double (&acc)[4]
 // DESCENDING order: own chunk `rel` feeds the column blocks <= rel, so after that step block `rel` is complete, and the
 // chunk's Phi tile in shared memory holds exactly the amplitudes of that block's columns for the row-dot epilogue.
 struct RhoStep {
-    int slab, i, nbp;
+    int slab, i, nbp, stride;  // a CTA visits the slabs slab, slab + stride, ... (stride = number of CTAs sharing a tile)
     __device__ __forceinline__ int nk() const { return nbp / kTileK; }
     __device__ __forceinline__ int first_chunk() const { return slab * (kTileN / kTileK); }
     __device__ __forceinline__ int count() const { return nk() - first_chunk(); }
@@ -143,20 +143,22 @@ struct RhoStep {
     __device__ __forceinline__ void advance() {
         if (++i == count()) {
             i = 0;
-            slab++;
+            slab += stride;
         }
     }
 };
 
-// grid = ceil(number of non-zero 32-point chunks / 4): a CTA's 128-row tile is made of four non-zero chunks
+// grid = (ceil(number of non-zero 32-point chunks / 4), nsplit): a CTA's 128-row tile is made of four non-zero chunks
 // (chunk_ids, padded to a multiple of 4 with -1 = unused row group).  Ph: zero-padded [nbp][nbp] density matrix with
-// halved 32x32 diagonal blocks (k_pad_P).  rho of skipped chunks stays 0.
+// halved 32x32 diagonal blocks (k_pad_P).  rho of skipped chunks stays 0.  With gridDim.y = nsplit > 1 the column slabs
+// of a tile are dealt round-robin to nsplit CTAs (finer work items when a rank holds only a few waves of tiles); CTA y
+// then writes its partial density to out + y * part_stride and k_rho_combine adds the parts in order.
 // 3 warpgroups: two of DMMA warps, one whose first warp is the producer.  384 threads start with 168 registers each;
 // the producer warpgroup hands its share back (setmaxnreg.dec) and the DMMA warpgroups grow to 232 (setmaxnreg.inc), so
 // the 128-register accumulator tile plus fragments and loop state never spill.
 __global__ void __launch_bounds__(kRhoTmaThreads, 1)
-k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const int* __restrict__ chunk_ids, double* __restrict__ rho, long nloc,
-          int nbp) {
+k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const int* __restrict__ chunk_ids, double* __restrict__ out, long part_stride,
+          long nloc, int nbp) {
     extern __shared__ __align__(128) double sm[];
     double* red = sm + (size_t)kStages * kRhoStageDoubles;  // [2][128]
     unsigned long long* full = reinterpret_cast<unsigned long long*>(red + 2 * kTileM);
@@ -173,8 +175,10 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
     const int* my_chunks = chunk_ids + 4 * (size_t)blockIdx.x;  // row group r (32 rows) of the tile = chunk my_chunks[r]
     const int nk = nbp / kTileK;
     const int nslab = (nbp + kTileN - 1) / kTileN;
+    const int sub = blockIdx.y, nsplit = gridDim.y;
     int total = 0;
-    for (int J = 0; J < nslab; J++) total += nk - J * (kTileN / kTileK);
+    for (int J = sub; J < nslab; J += nsplit) total += nk - J * (kTileN / kTileK);
+    double* rho = out + (size_t)sub * part_stride;
 
     if (warp >= 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
@@ -182,7 +186,7 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
         // and 8 of the 32 rows of the Ph block.  A bulk copy costs the issuing warp ~50 clocks, so one warp alone
         // (160 copies per stage) cannot keep up with the short in-slab steps.
         const int j = warp - 8;
-        RhoStep ld{0, 0, nbp};
+        RhoStep ld{sub, 0, nbp, nsplit};
         const double* grp = phi + ((size_t)max(my_chunks[j], 0) * kTileK + lane) * (size_t)nbp;  // unused group: any valid rows
         for (int it = 0; it < total; it++) {
             const unsigned stage = (unsigned)it % kStages, round = (unsigned)it / kStages;
@@ -210,7 +214,7 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
     const long p0w = (long)max(my_chunk, 0) * kTileK;
     double rowsum[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][8][2];
-    RhoStep cs{0, 0, nbp};
+    RhoStep cs{sub, 0, nbp, nsplit};
     for (int it = 0; it < total; it++) {
         const unsigned stage = (unsigned)it % kStages, round = (unsigned)it / kStages;
         const int nblk = cs.nblk();
@@ -273,6 +277,15 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
         const long p = (long)c * kTileK + (tid & 31);
         if (c >= 0 && p < nloc) rho[p] = 4.0 * (red[tid] + red[kTileM + tid]);
     }
+}
+
+// rho = part_0 + part_1 (+ part_2): the partial densities of a tile's nsplit CTAs, added in a fixed order.
+__global__ void k_rho_combine(const double* __restrict__ part, long part_stride, int nsplit, long nloc, double* __restrict__ rho) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nloc) return;
+    double v = part[p];
+    for (int s = 1; s < nsplit; s++) v += part[(size_t)s * part_stride + p];
+    rho[p] = v;
 }
 
 // =========================================================================================================

@@ -383,7 +383,7 @@ k_interp_t(GridShape g, const double* __restrict__ atom_xyz, const double* __res
            const double* __restrict__ pz, const double* __restrict__ w, const double* __restrict__ Vown,
            const double* __restrict__ xs, const double* __restrict__ pre, const double* __restrict__ coef,
            double* __restrict__ Vpart /*[gridDim.y][nloc]*/) {
-    extern __shared__ __align__(32) double sm[];
+    extern __shared__ __align__(128) double sm[];
     const int N = g.nrad;
     constexpr int NLM = (L + 1) * (L + 1);
     // Spline-record staging: the 32 points of a warp usually fall into one or two adjacent radial intervals of a source
@@ -607,7 +607,7 @@ k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __r
              const double* __restrict__ pz, const double* __restrict__ xs, const double* __restrict__ coef,
              const int* __restrict__ item_key, const int* __restrict__ pair_point, long nitems, double* __restrict__ out) {
     constexpr int NLM = (L + 1) * (L + 1);
-    extern __shared__ __align__(32) double sm[];
+    extern __shared__ __align__(128) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long item = (long)blockIdx.x * kBinWarps + warp;
     if (item >= nitems) return;

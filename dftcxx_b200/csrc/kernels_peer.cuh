@@ -106,8 +106,10 @@ __global__ void k_contract_reduce_publish(const double* __restrict__ partial, co
     }
 }
 
-// out[i] = sum over ranks (ascending) of contrib_r[i], i < n.  Any grid size; every CTA waits for the publications.
-__global__ void k_peer_sum(PeerSet ps, unsigned long long epoch, size_t n, double* __restrict__ out) {
+// out = sum over ranks (ascending) of contrib_r for the nmat symmetric nb x nb matrices stored back to back: only the
+// upper triangles travel over NVLink, the lower ones are mirrored locally.  Any grid size; every CTA waits for the
+// publications.
+__global__ void k_peer_sum(PeerSet ps, unsigned long long epoch, int nb, int nmat, double* __restrict__ out) {
     __shared__ bool ok;
     PeerHeader* me = peer_header(ps, ps.rank);
     if (threadIdx.x == 0) {
@@ -116,12 +118,17 @@ __global__ void k_peer_sum(PeerSet ps, unsigned long long epoch, size_t n, doubl
     }
     __syncthreads();
     if (ok) {
+        const size_t nb2 = (size_t)nb * nb, n = nb2 * nmat;
         const double* src[kPeerMaxRanks];
         for (int r = 0; r < ps.nranks; r++) src[r] = peer_contrib(ps, r, epoch, n);
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+            const size_t m = t / nb2, e = t - m * nb2;
+            const int i = (int)(e / nb), j = (int)(e - (size_t)i * nb);
+            if (j < i) continue;
             double s = 0.0;
-            for (int r = 0; r < ps.nranks; r++) s += __ldcg(src[r] + i);  // L2-coherent loads: never a stale L1 line
-            out[i] = s;
+            for (int r = 0; r < ps.nranks; r++) s += __ldcg(src[r] + t);  // L2-coherent loads: never a stale L1 line
+            out[t] = s;
+            out[m * nb2 + (size_t)j * nb + i] = s;
         }
     }
     __threadfence_system();
