@@ -274,9 +274,11 @@ def main():
     g.upload_density(P)
     for _ in range(args.warmup):
         g.iteration_device()
+    # the clock sampler forks nvidia-smi (tens of ms from a process this size): start it BEFORE the barrier, otherwise the
+    # other ranks' timers include rank 0's fork while they wait for it in the first collective
+    sampler = ClockSampler(local) if rank == 0 else None
     g.synchronize()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     n0 = g.launch_count()
     if small:
         # small inputs: flush L2 between steps, time each step separately
