@@ -231,30 +231,37 @@ float elapsed(dftgrid* h, int a, int b) {
 // Stream-K schedule of the [XC | J] contraction (see kernels_dense.cuh): the items' costs for ONE chunk are laid end to
 // end and cut into equal shares, one per CTA (one CTA per SM); a share is 1-3 segments given as fixed-point fractions
 // of the item's chunks (which chunks those are is decided on the device by a low-discrepancy hash).
-void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
-    cudaStream_t st = h->stream;
-    std::vector<int> pairs;
-    const int nt = (h->nbp + kTileM - 1) / kTileM;
+struct ContractSchedule {
+    std::vector<int> pairs;     // [npairs][2] upper-triangular tile pairs
+    std::vector<ConSeg> segs;   // CTA after CTA; an item's segments are consecutive
+    std::vector<int> cta_off;   // [nctas+1] into segs
+    std::vector<int> item_off;  // [nitems+1] into segs, item = z * npairs + pair
+    int npairs = 0, bc = 1;
+};
+
+// Pure host arithmetic (no device): also exported as dftgrid_debug_contract_schedule for the CPU test-suite.
+void compute_contract_schedule(int nbp, long nchunk, int nsm, ContractSchedule& S) {
+    S = ContractSchedule();
+    const int nt = (nbp + kTileM - 1) / kTileM;
     for (int i = 0; i < nt; i++)
         for (int j = i; j < nt; j++) {
-            pairs.push_back(i);
-            pairs.push_back(j);
+            S.pairs.push_back(i);
+            S.pairs.push_back(j);
         }
-    h->npairs = (int)pairs.size() / 2;
-    h->d_pairs.upload(pairs, st);
-    const int nitems = 2 * h->npairs;
+    S.npairs = (int)S.pairs.size() / 2;
+    const int npairs = S.npairs, nitems = 2 * npairs;
     std::vector<double> cost(nitems);
     double W1 = 0.0;  // cost of all items for one chunk
     for (int it = 0; it < nitems; it++) {
-        const int ti = pairs[2 * (it % h->npairs)], tj = pairs[2 * (it % h->npairs) + 1];
+        const int ti = S.pairs[2 * (it % npairs)], tj = S.pairs[2 * (it % npairs) + 1];
         // relative cost of one k-chunk of this tile pair (full off-diagonal 128x128 tile = 20), calibrated by sweeps at
         // (H2O)64, (H2O)32 and C40H82: a 64-wide edge tile issues half the DMMAs but pays the same loads (10.5), a
         // diagonal tile issues 17 of 32 DMMAs per warp (11.5), the 64-wide diagonal tile 8 of 32 (6.5; under-estimating
         // it makes its CTA the straggler, 5 costs 14 %)
         const char* nc = std::getenv("DFTGRID_NARROW_COST");
         const char* dc = std::getenv("DFTGRID_DIAG_COST");
-        const bool narrow = std::min(kTileN, h->nbp - tj * kTileN) <= 64;
         const char* ec = std::getenv("DFTGRID_EDGE_DIAG_COST");
+        const bool narrow = std::min(kTileN, nbp - tj * kTileN) <= 64;
         const double c_narrow = nc ? std::atof(nc) : 10.5, c_diag = dc ? std::atof(dc) : 11.5, c_edge_diag = ec ? std::atof(ec) : 6.5;
         cost[it] = ti == tj ? (narrow ? c_edge_diag : c_diag) : (narrow ? c_narrow : 20.0);
         W1 += cost[it];
@@ -263,7 +270,7 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
     // Measured at (H2O)64: DRAM reads 15.1 GB without blocks, 9.8 GB with 80-160 MB blocks, 10.3 GB at 40 MB where the
     // accumulator parking starts to cost time; at least 64 chunks; one block when the shard is smaller.
     {
-        const double chunk_bytes = (double)kTileK * h->nbp * sizeof(double);
+        const double chunk_bytes = (double)kTileK * nbp * sizeof(double);
         double l2_mb = 120.0;
         if (const char* e = std::getenv("DFTGRID_L2_BLOCK_MB")) l2_mb = std::atof(e);  // developer sweep; <= 0: one block
         long bc = l2_mb > 0 ? (long)(l2_mb * 1e6 / chunk_bytes) : nchunk;
@@ -271,20 +278,19 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
         if (bc >= nchunk) bc = std::max<long>(nchunk, 1);
         const long nblock = (nchunk + bc - 1) / bc;
         if (nblock > 0) bc = (nchunk + nblock - 1) / nblock;  // equal blocks
-        h->con_bc = (int)bc;
+        S.bc = (int)bc;
     }
     const double W = W1 * (double)nchunk;
     const int G = (int)std::max<long>(1, std::min<long>(nsm, (long)(W / 40.0) > 0 ? (long)(W / 40.0) : 1));
-    std::vector<ConSeg> segs;
-    std::vector<int> cta_off(1, 0), item_off(nitems + 1, 0);
-    // cumulative cost positions: item `it` occupies [start[it], start[it] + cost[it]) of [0, W1)
+    S.cta_off.assign(1, 0);
+    S.item_off.assign(nitems + 1, 0);
+    // cumulative cost positions: item `it` occupies [start, start + cost[it]) of [0, W1)
     {
         int it = 0;
         double start = 0.0;
         for (int c = 0; c < G; c++) {
             const double lo = W1 * c / G, hi = c == G - 1 ? W1 : W1 * (c + 1) / G;
-            // items overlapping [lo, hi)
-            while (it < nitems && start + cost[it] <= lo) {
+            while (it < nitems && start + cost[it] <= lo) {  // items that end before this share
                 start += cost[it];
                 it++;
             }
@@ -299,33 +305,42 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
             };
             while (j < nitems && sj < hi) {
                 const unsigned tb = frac(lo, sj, cost[j]), te = frac(hi, sj, cost[j]);
-                if (te > tb) segs.push_back(ConSeg{j / h->npairs, j % h->npairs, tb, te});
+                if (te > tb) S.segs.push_back(ConSeg{j / npairs, j % npairs, tb, te});
                 sj += cost[j];
                 j++;
             }
-            cta_off.push_back((int)segs.size());
+            S.cta_off.push_back((int)S.segs.size());
         }
     }
     // A boundary W1*c/G is the same double for the share ending there and the share starting there, and the item starts
-    // are exact sums of small integers, so fe of one segment == fb of the next bit for bit.  Segments are emitted CTA
+    // are exact sums of small numbers, so te of one segment == tb of the next bit for bit.  Segments are emitted CTA
     // after CTA in item-major order, hence an item's segments are consecutive: item_off indexes `segs` directly.
     {
         int pos = 0;
         for (int it = 0; it < nitems; it++) {
-            item_off[it] = pos;
-            while (pos < (int)segs.size() && segs[pos].z * h->npairs + segs[pos].pair == it) pos++;
+            S.item_off[it] = pos;
+            while (pos < (int)S.segs.size() && S.segs[pos].z * npairs + S.segs[pos].pair == it) pos++;
         }
-        item_off[nitems] = pos;
-        if (pos != (int)segs.size()) throw std::runtime_error("internal error: contraction segments are not item-major");
+        S.item_off[nitems] = pos;
+        if (pos != (int)S.segs.size()) throw std::runtime_error("internal error: contraction segments are not item-major");
     }
-    h->con_ctas = (int)cta_off.size() - 1;
-    h->nsplit = (int)segs.size();
-    h->d_segs.alloc(segs.size());
-    CK(cudaMemcpyAsync(h->d_segs.p, segs.data(), segs.size() * sizeof(ConSeg), cudaMemcpyHostToDevice, st));
-    h->d_cta_off.upload(cta_off, st);
-    h->d_item_off.upload(item_off, st);
-    h->d_partial.alloc((size_t)segs.size() * kTileM * kTileN);
-    CK(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+}
+
+void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
+    cudaStream_t st = h->stream;
+    ContractSchedule S;
+    compute_contract_schedule(h->nbp, nchunk, nsm, S);
+    h->npairs = S.npairs;
+    h->con_bc = S.bc;
+    h->d_pairs.upload(S.pairs, st);
+    h->con_ctas = (int)S.cta_off.size() - 1;
+    h->nsplit = (int)S.segs.size();
+    h->d_segs.alloc(S.segs.size());
+    CK(cudaMemcpyAsync(h->d_segs.p, S.segs.data(), S.segs.size() * sizeof(ConSeg), cudaMemcpyHostToDevice, st));
+    h->d_cta_off.upload(S.cta_off, st);
+    h->d_item_off.upload(S.item_off, st);
+    h->d_partial.alloc((size_t)S.segs.size() * kTileM * kTileN);
+    CK(cudaStreamSynchronize(st));  // S goes out of scope
 }
 
 // Lists of the 32-point chunks / 128-point tiles of Phi that hold any non-zero amplitude (k_chunk_flags), and the
@@ -1211,5 +1226,26 @@ int dftgrid_timer_stop(dftgrid_t* h, double* ms) {
 }
 
 long dftgrid_launch_count(const dftgrid_t* h) { return h->launches; }
+
+int dftgrid_debug_contract_schedule(int nbp, long nchunk, int nsm, int max_segs, int* segs_out, int* cta_off_out, int* nctas, int* nsegs,
+                                    int* block_chunks) {
+    return guarded([&] {
+        if (nbp <= 0 || nbp % kNbAlign != 0 || nchunk < 0 || nsm <= 0 || !segs_out || !cta_off_out || !nctas || !nsegs || !block_chunks)
+            throw std::runtime_error("dftgrid_debug_contract_schedule: bad arguments");
+        ContractSchedule S;
+        compute_contract_schedule(nbp, nchunk, nsm, S);
+        if ((int)S.segs.size() > max_segs) throw std::runtime_error("dftgrid_debug_contract_schedule: max_segs too small");
+        for (size_t i = 0; i < S.segs.size(); i++) {
+            segs_out[4 * i + 0] = S.segs[i].z;
+            segs_out[4 * i + 1] = S.segs[i].pair;
+            std::memcpy(&segs_out[4 * i + 2], &S.segs[i].tb, sizeof(unsigned));
+            std::memcpy(&segs_out[4 * i + 3], &S.segs[i].te, sizeof(unsigned));
+        }
+        for (size_t i = 0; i < S.cta_off.size(); i++) cta_off_out[i] = S.cta_off[i];
+        *nctas = (int)S.cta_off.size() - 1;
+        *nsegs = (int)S.segs.size();
+        *block_chunks = S.bc;
+    });
+}
 
 }  // extern "C"

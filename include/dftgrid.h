@@ -139,6 +139,13 @@ int dftgrid_timer_stop(dftgrid_t* h, double* ms);
 /* Kernel launches issued by this handle since creation. */
 long dftgrid_launch_count(const dftgrid_t* h);
 
+/* Test hook, pure host arithmetic (no device needed): the stream-K schedule the [J | XC] contraction would use for a padded
+ * basis size nbp (multiple of 32), nchunk non-zero 32-point chunks and nsm SMs.  segs_out: [nsegs][4] = (matrix, tile pair,
+ * begin, end) with begin/end 31-bit fixed-point fractions of the item's chunks; cta_off_out: [nctas+1] (caller provides
+ * nsm+1 ints).  Chunk x belongs to the segment whose [begin, end) holds ((x * 2654435769) mod 2^32) >> 1. */
+int dftgrid_debug_contract_schedule(int nbp, long nchunk, int nsm, int max_segs, int* segs_out, int* cta_off_out, int* nctas, int* nsegs,
+                                    int* block_chunks);
+
 enum {
     DFTGRID_T_POINTS = 0,   /* build: points + raw weights            */
     DFTGRID_T_BECKE = 1,    /* build: Becke fuzzy-cell weights        */
