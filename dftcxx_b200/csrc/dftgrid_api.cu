@@ -130,6 +130,13 @@ struct dftgrid {
     bool peer_ready = false;
     unsigned long long peer_epoch = 0;
 
+    // CUDA graph of one whole iteration (single-GPU handles): the 15 launches of a small molecule's iteration are
+    // launch-latency bound, one graph launch replaces them from the second call of dftgrid_iteration_device on
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool capturing = false, graph_failed = false;
+    long eager_iterations = 0, graph_launches_per_iter = 0;
+
     // timing
     cudaEvent_t ev[16]{};
     cudaEvent_t ev_sw[2]{};
@@ -137,6 +144,8 @@ struct dftgrid {
     double t_ms[DFTGRID_T_COUNT]{};
 
     ~dftgrid() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (graph) cudaGraphDestroy(graph);
         for (void* m : peer_mapped) cudaIpcCloseMemHandle(m);
         if (xbuf) cudaFree(xbuf);
         if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
@@ -220,7 +229,14 @@ void prepare_basis(dftgrid* h, const dftgrid_system* s) {
     for (int t = 0; t < s->nprim; t++) h->prim_exp[t] = h->center_exp_off[prim_center[t]] + prim_local[t];
 }
 
-void record(dftgrid* h, int i) { CK(cudaEventRecord(h->ev[i], h->stream)); }
+// Phase-timer events.  While the iteration is being captured into a CUDA graph the record becomes an external event
+// node, so the events are really recorded at every replay and cudaEventElapsedTime keeps working.
+void record(dftgrid* h, int i) {
+    if (h->capturing)
+        CK(cudaEventRecordWithFlags(h->ev[i], h->stream, cudaEventRecordExternal));
+    else
+        CK(cudaEventRecord(h->ev[i], h->stream));
+}
 
 float elapsed(dftgrid* h, int a, int b) {
     float ms = 0.f;
@@ -1112,9 +1128,55 @@ int dftgrid_iteration_device(dftgrid_t* h) {
     return guarded([&] {
         use_device(h);
         if (!h->built) throw std::runtime_error("dftgrid_build has not been called");
+        static const bool no_graph = std::getenv("DFTGRID_NO_GRAPH") != nullptr;  // developer A/B switch
+        const bool want_graph = h->nranks == 1 && !no_graph && !h->graph_failed;
+        if (want_graph && h->graph_exec) {
+            CK(cudaGraphLaunch(h->graph_exec, h->stream));
+            h->launches += h->graph_launches_per_iter;
+            h->have_density = h->have_potential = h->contract_valid = h->timed_iter = true;
+            return;
+        }
+        if (want_graph && h->eager_iterations >= 1) {
+            // the first iteration ran eagerly (every lazily sized buffer exists now): capture the second one
+            const long l0 = h->launches;
+            bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                h->capturing = true;
+                try {
+                    run_density(h);
+                    run_potential(h);
+                    run_contract(h);
+                } catch (...) {
+                    ok = false;
+                }
+                h->capturing = false;
+                cudaGraph_t gcap = nullptr;
+                if (cudaStreamEndCapture(h->stream, &gcap) != cudaSuccess || !gcap) ok = false;
+                if (ok && cudaGraphInstantiate(&h->graph_exec, gcap, 0) != cudaSuccess) ok = false;
+                if (ok) {
+                    h->graph = gcap;
+                    h->graph_launches_per_iter = h->launches - l0;
+                    h->launches = l0;
+                } else if (gcap) {
+                    cudaGraphDestroy(gcap);
+                }
+            }
+            if (!ok) {
+                cudaGetLastError();
+                h->graph_exec = nullptr;
+                h->graph_failed = true;  // stay on eager launches
+                h->launches = l0;
+            } else {
+                CK(cudaGraphLaunch(h->graph_exec, h->stream));
+                h->launches += h->graph_launches_per_iter;
+                h->have_density = h->have_potential = h->contract_valid = h->timed_iter = true;
+                return;
+            }
+        }
         run_density(h);
         run_potential(h);
         run_contract(h);
+        h->eager_iterations++;
         CK(cudaGetLastError());
     });
 }
