@@ -260,9 +260,7 @@ def main():
     peer_path = False
     if world > 1 and not args.no_peer:
         # the [J | XC] sum runs in the library's own peer-memory kernels when the ranks' GPUs have a P2P path
-        hs = [None] * world
-        dist.all_gather_object(hs, g.peer_export())
-        peer_path = g.peer_connect(hs)
+        peer_path = g.connect_peers(dist)  # all ranks agree: peer path only if every rank mapped every buffer
     tb = g.timings()
     P = systems.synthetic_density(mol)
     flush = None

@@ -1050,6 +1050,14 @@ int dftgrid_peer_connect(dftgrid_t* h, const void* handles) {
 
 int dftgrid_peer_active(const dftgrid_t* h) { return h->peer_ready ? 1 : 0; }
 
+int dftgrid_peer_disable(dftgrid_t* h) {
+    return guarded([&] {
+        use_device(h);
+        CK(cudaStreamSynchronize(h->stream));
+        h->peer_ready = false;  // back to ncclAllReduce; the mappings stay open until the handle is destroyed
+    });
+}
+
 int dftgrid_build(dftgrid_t* h) {
     return guarded([&] {
         use_device(h);

@@ -48,6 +48,7 @@ def lib():
     L.dftgrid_peer_export.argtypes = [C.c_void_p, C.c_void_p]
     L.dftgrid_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
     L.dftgrid_peer_active.argtypes = [C.c_void_p]
+    L.dftgrid_peer_disable.argtypes = [C.c_void_p]
     L.dftgrid_timer_stop.argtypes = [C.c_void_p, _dp]
     for n in ("dftgrid_build", "dftgrid_iteration_device", "dftgrid_synchronize", "dftgrid_timer_start"):
         getattr(L, n).argtypes = [C.c_void_p]
@@ -159,6 +160,27 @@ class MolecularGrid:
             raise GridError("peer_connect needs one 64-byte handle per rank")
         rc = lib().dftgrid_peer_connect(self.h, blob)
         return rc == 0 and lib().dftgrid_peer_active(self.h) == 1
+
+    def peer_disable(self):
+        """Back to ncclAllReduce for the [J | XC] sum.  Every rank must make the same choice: call this on all ranks when
+        peer_connect returned False on any of them (see connect_peers)."""
+        self._ck(lib().dftgrid_peer_disable(self.h))
+
+    def connect_peers(self, dist):
+        """Collective helper for torch.distributed hosts: exchange the IPC handles, map them, and keep the peer-memory
+        path only if the mapping succeeded on EVERY rank.  Returns True when the peer path is active."""
+        import torch
+
+        hs = [None] * self.nranks
+        dist.all_gather_object(hs, self.peer_export())
+        ok = self.peer_connect(hs)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda:%d" % self.device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if ok:
+                self.peer_disable()
+            return False
+        return True
 
     def set_density(self, P):
         """set_density + correct_densities (src/moleculargrid.cpp:48-53,132-146)."""

@@ -83,6 +83,9 @@ int dftgrid_comm_init(dftgrid_t* h, const void* id128);
 int dftgrid_peer_export(dftgrid_t* h, void* handle64);
 int dftgrid_peer_connect(dftgrid_t* h, const void* handles /* [nranks][64] */);
 int dftgrid_peer_active(const dftgrid_t* h);
+/* The choice between the peer-memory path and NCCL must be the same on every rank: if dftgrid_peer_connect failed on
+ * ANY rank (the host checks, e.g. with an all-reduce(min) of the return codes), every rank calls dftgrid_peer_disable. */
+int dftgrid_peer_disable(dftgrid_t* h);
 
 /* MolecularGrid::create_grid (src/moleculargrid.cpp:193-261): points, quadrature weights, CGF amplitudes,
  * Becke weights; also factorises the radial Poisson operators used by dftgrid_hartree_J. */

@@ -59,9 +59,7 @@ def parity(name):
     J, XC, exc, nel = mg.iteration(g["P"])  # last collective through ncclAllReduce
     peer = False
     if os.environ.get("DFTGRID_TEST_PEER", "1") == "1":
-        hs = [None] * world
-        dist.all_gather_object(hs, mg.peer_export())
-        peer = mg.peer_connect(hs)
+        peer = mg.connect_peers(dist)
         for _ in range(3):  # several epochs: the exchange buffers alternate and are re-used
             Jp, XCp, excp, nelp = mg.iteration(g["P"])
         # the NCCL ring/tree and the rank-ordered peer sum may round differently; both are within the parity tolerance
