@@ -100,7 +100,8 @@ void DFT::calculate_density_matrix() {
     C = matmul(X, Cc);
     const unsigned int nocc = nelec / 2;
     Mat Pnew(n, n, 0.0);
-    for (unsigned int i = 0; i < n; i++)
+#pragma omp parallel for schedule(static) if (n > 64)
+    for (long i = 0; i < (long)n; i++)
         for (unsigned int j = 0; j < n; j++) {
             double s = 0.0;
             for (unsigned int k = 0; k < nocc; k++) s += C(i, k) * C(j, k);

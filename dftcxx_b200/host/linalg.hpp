@@ -1,6 +1,8 @@
 // Small dense linear algebra for the host SCF driver (the reference leans on Eigen, which this build does not
 // need): a row-major matrix, products, and a symmetric eigen-solver (Householder tridiagonalisation followed by
 // implicit-shift QL), eigenvalues ascending like Eigen::SelfAdjointEigenSolver (reference src/dft.cpp:303,339).
+// The O(n^3) loops are OpenMP-parallel over independent rows / columns; every element is still computed by the same
+// sequence of operations as in the serial algorithm, so results do not depend on the thread count.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -31,13 +33,24 @@ inline Mat matmul(const Mat& a, const Mat& b) {
     if (a.cols() != b.rows()) throw std::runtime_error("matmul: shape mismatch");
     Mat c(a.rows(), b.cols(), 0.0);
     const size_t n = a.rows(), m = b.cols(), k = a.cols();
-    for (size_t i = 0; i < n; i++)
-        for (size_t l = 0; l < k; l++) {
-            const double ail = a(i, l);
-            const double* br = b.data() + l * m;
-            double* cr = c.data() + i * m;
-            for (size_t j = 0; j < m; j++) cr[j] += ail * br[j];
+    // c(i,j) = sum_l a(i,l) b(l,j) with l ascending for every element; blocked 4 rows x 256 columns so that a strip of b
+    // is reused by four rows while their c strip stays in L1
+    constexpr size_t RB = 4, CB = 256;
+#pragma omp parallel for schedule(static) if (n * m * k > 200000)
+    for (long ib = 0; ib < (long)((n + RB - 1) / RB); ib++) {
+        const size_t i0 = (size_t)ib * RB, i1 = std::min(n, i0 + RB);
+        for (size_t j0 = 0; j0 < m; j0 += CB) {
+            const size_t j1 = std::min(m, j0 + CB);
+            for (size_t l = 0; l < k; l++) {
+                const double* br = b.data() + l * m;
+                for (size_t i = i0; i < i1; i++) {
+                    const double ail = a(i, l);
+                    double* cr = c.data() + i * m;
+                    for (size_t j = j0; j < j1; j++) cr[j] += ail * br[j];
+                }
+            }
         }
+    }
     return c;
 }
 
@@ -61,7 +74,7 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
     if ((int)A.cols() != n) throw std::runtime_error("sym_eigen: matrix not square");
     V = A;
     w.assign(n, 0.0);
-    std::vector<double> e(n, 0.0);
+    std::vector<double> e(n, 0.0), rot_s, rot_c, gvec;
     if (n == 0) return;
     // --- Householder reduction to tridiagonal form, accumulating the orthogonal transformation in V
     for (int i = n - 1; i > 0; i--) {
@@ -81,20 +94,40 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
                 e[i] = scale * g;
                 h -= f * g;
                 V(i, l) = f - g;
-                f = 0.0;
-                for (int j = 0; j <= l; j++) {
-                    V(j, i) = V(i, j) / h;
-                    g = 0.0;
-                    for (int k = 0; k <= j; k++) g += V(j, k) * V(i, k);
-                    for (int k = j + 1; k <= l; k++) g += V(k, j) * V(i, k);
-                    e[j] = g / h;
-                    f += e[j] * V(i, j);
+                // e = A v / h over the stored lower triangle: e_j = sum_{k<=j} A(j,k) v_k + sum_{k>j} A(k,j) v_k, every sum
+                // in ascending k.  The second part is gathered row by row (contiguous) instead of down column j; threads
+                // own ranges of j.
+#pragma omp parallel if (l > 96)
+                {
+#pragma omp for schedule(dynamic, 16)
+                    for (int j = 0; j <= l; j++) {
+                        V(j, i) = V(i, j) / h;
+                        double gj = 0.0;
+                        for (int k = 0; k <= j; k++) gj += V(j, k) * V(i, k);
+                        e[j] = gj;
+                    }
+#pragma omp for schedule(static)
+                    for (int jb = 0; jb <= l; jb += 64) {
+                        const int je = std::min(jb + 64, l + 1);
+                        for (int k = jb + 1; k <= l; k++) {
+                            const double vk = V(i, k);
+                            const double* rk = &V(k, 0);
+                            const int jmax = std::min(je, k);
+                            for (int j = jb; j < jmax; j++) e[j] += rk[j] * vk;
+                        }
+                    }
+#pragma omp for schedule(static)
+                    for (int j = 0; j <= l; j++) e[j] /= h;
                 }
+                f = 0.0;
+                for (int j = 0; j <= l; j++) f += e[j] * V(i, j);
                 const double hh = f / (h + h);
+                for (int j = 0; j <= l; j++) e[j] -= hh * V(i, j);
+                // rank-2 update of the lower triangle, row by row
+#pragma omp parallel for schedule(dynamic, 16) if (l > 96)
                 for (int j = 0; j <= l; j++) {
-                    f = V(i, j);
-                    e[j] = g = e[j] - hh * f;
-                    for (int k = 0; k <= j; k++) V(j, k) -= f * e[k] + g * V(i, k);
+                    const double fj = V(i, j), gj = e[j];
+                    for (int k = 0; k <= j; k++) V(j, k) -= fj * e[k] + gj * V(i, k);
                 }
             }
         } else {
@@ -107,10 +140,25 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
     for (int i = 0; i < n; i++) {
         const int l = i - 1;
         if (w[i] != 0.0) {
-            for (int j = 0; j <= l; j++) {
-                double g = 0.0;
-                for (int k = 0; k <= l; k++) g += V(i, k) * V(k, j);
-                for (int k = 0; k <= l; k++) V(k, j) -= g * V(k, i);
+            // g_j = sum_k V(i,k) V(k,j) (ascending k), then V(k,j) -= g_j V(k,i): both walked along rows
+            gvec.assign(l + 1, 0.0);
+#pragma omp parallel if (l > 96)
+            {
+#pragma omp for schedule(static)
+                for (int jb = 0; jb <= l; jb += 64) {
+                    const int je = std::min(jb + 64, l + 1);
+                    for (int k = 0; k <= l; k++) {
+                        const double vik = V(i, k);
+                        const double* rk = &V(k, 0);
+                        for (int j = jb; j < je; j++) gvec[j] += vik * rk[j];
+                    }
+                }
+#pragma omp for schedule(static)
+                for (int k = 0; k <= l; k++) {
+                    const double vki = V(k, i);
+                    double* rk = &V(k, 0);
+                    for (int j = 0; j <= l; j++) rk[j] -= gvec[j] * vki;
+                }
             }
         }
         w[i] = V(i, i);
@@ -134,6 +182,11 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
                 g = w[m] - w[l] + e[l] / (g + (g >= 0.0 ? std::fabs(r) : -std::fabs(r)));
                 double s = 1.0, c = 1.0, p = 0.0;
                 int i;
+                // the sweep's plane rotations are recorded and then applied to the eigenvector rows in parallel: row k
+                // sees them in the same order as in the serial algorithm
+                rot_s.clear();
+                rot_c.clear();
+                const int i_first = m - 1;
                 for (i = m - 1; i >= l; i--) {
                     double f = s * e[i];
                     const double b = c * e[i];
@@ -149,10 +202,20 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
                     r = (w[i] - g) * s + 2.0 * c * b;
                     w[i + 1] = g + (p = s * r);
                     g = c * r - b;
+                    rot_s.push_back(s);
+                    rot_c.push_back(c);
+                }
+                {
+                    const int nrot = (int)rot_s.size();
+#pragma omp parallel for schedule(static) if ((long)nrot * n > 20000)
                     for (int k = 0; k < n; k++) {
-                        f = V(k, i + 1);
-                        V(k, i + 1) = s * V(k, i) + c * f;
-                        V(k, i) = c * V(k, i) - s * f;
+                        double* row = &V(k, 0);
+                        for (int t = 0; t < nrot; t++) {
+                            const int ii = i_first - t;
+                            const double fk = row[ii + 1];
+                            row[ii + 1] = rot_s[t] * row[ii] + rot_c[t] * fk;
+                            row[ii] = rot_c[t] * row[ii] - rot_s[t] * fk;
+                        }
                     }
                 }
                 if (r == 0.0 && i >= l) continue;
