@@ -327,3 +327,30 @@ def test_contraction_schedule_tiles_every_item_exactly_once(nbp, nchunk, nsm):
         share = [sum(cost(int(pair[s])) * (te[s] - tb[s]) / float(1 << 31) for s in range(cta_off[c], cta_off[c + 1])) for c in range(nctas.value)]
         assert max(share) - min(share) <= 1e-6 * max(share)
         assert max(np.diff(cta_off[:nctas.value + 1])) <= 4 or nctas.value < 2 * npairs
+
+
+def test_host_eigensolver_is_thread_count_independent():
+    """The OpenMP-parallel host eigen-solver keeps the serial algorithm's per-element operation order: same bits with 1 and 4
+    threads (n above the parallel thresholds), and a sane decomposition."""
+    import hashlib
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, hashlib, ctypes, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from test_cpu import _hostlib\n"
+        "L, dp = _hostlib()\n"
+        "n = 260\n"
+        "A = np.random.default_rng(11).standard_normal((n, n)); A = A + A.T\n"
+        "w, V = np.zeros(n), np.zeros((n, n))\n"
+        "assert L.dfthost_sym_eigen(n, np.ascontiguousarray(A).ctypes.data_as(dp), w.ctypes.data_as(dp), V.ctypes.data_as(dp)) == 0\n"
+        "assert np.max(np.abs(A @ V - V * w)) < 1e-11 * n\n"
+        "print(hashlib.sha256(w.tobytes() + V.tobytes()).hexdigest())\n" % (ROOT, os.path.join(ROOT, "tests")))
+    digests = []
+    for threads in ("1", "4"):
+        env = dict(os.environ, OMP_NUM_THREADS=threads)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
