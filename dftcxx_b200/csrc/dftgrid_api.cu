@@ -3,6 +3,7 @@
 #include "../../include/dftgrid.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -964,6 +965,22 @@ void dftgrid_destroy(dftgrid_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->peer_ready && h->peer_epoch > 0) {
+        // another rank may still be summing this rank's exchange buffer (its k_peer_sum of the last epoch): wait, bounded,
+        // until every peer has written consumed_by[peer] >= the last epoch into THIS rank's header, then free it
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < h->peers.nranks; r++) {
+            if (r == h->rank) continue;
+            unsigned long long consumed = 0;
+            do {
+                if (cudaMemcpy(&consumed, h->xbuf + offsetof(PeerHeader, consumed_by) + r * sizeof(unsigned long long), sizeof consumed,
+                               cudaMemcpyDeviceToHost) != cudaSuccess) {
+                    cudaGetLastError();
+                    break;
+                }
+            } while (consumed < h->peer_epoch && std::chrono::steady_clock::now() - t0 < std::chrono::seconds(5));
+        }
+    }
     delete h;
 }
 

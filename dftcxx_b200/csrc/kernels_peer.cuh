@@ -2,17 +2,18 @@
 // k_contract_reduce + ncclAllReduce when every rank's exchange buffer has been mapped (dftgrid_peer_connect).
 //
 // Every rank owns one exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle):
-//   header  : ready    (u64) number of contraction epochs whose contribution is published
-//             consumed (u64) number of epochs this rank has finished summing
-//             error    (u64) set when a spin-wait timed out (the host turns it into an error)
-//             ticket   (u32 x 2) last-CTA election counters of the two kernels
+//   header  : ready          (u64) number of contraction epochs whose contribution is published
+//             error          (u64) set when a spin-wait timed out (the host turns it into an error)
+//             ticket         (u32 x 2) last-CTA election counters of the two kernels
+//             consumed_by[r] (u64) number of epochs rank r has finished summing — written BY rank r INTO this buffer, so
+//                            the owner polls only its own memory (also at teardown, before it frees the buffer)
 //   contrib : [2][2 nb^2] doubles, indexed by epoch parity; [J | XC] of this rank's points, full matrices.
 //
 // k_contract_reduce_publish : fixed-order sum of the stream-K partial tiles (as k_contract_reduce) into contrib[e];
 //                             the last CTA to finish publishes ready = epoch with a system-scope release.
 // k_peer_sum                : waits until every rank has published the epoch, then out[i] = sum_r contrib_r[e][i] in
 //                             rank order (identical bits on every rank), reading the peers' buffers directly over
-//                             NVLink; the last CTA publishes consumed = epoch.
+//                             NVLink; the last CTA writes consumed_by[this rank] = epoch into every rank's header.
 // A contribution buffer is reused two epochs later; the publisher first waits until every peer has consumed epoch-2.
 // All spin-waits are bounded (kPeerSpinLimit clocks): a lost peer raises the error flag instead of hanging the GPU.
 #pragma once
@@ -26,9 +27,11 @@ constexpr long long kPeerSpinLimit = 20000000000LL;  // ~10 s at 2 GHz
 constexpr size_t kPeerHeaderBytes = 256;
 
 struct PeerHeader {
-    unsigned long long ready, consumed, error;
+    unsigned long long ready, error;
     unsigned int ticket[2];
+    unsigned long long consumed_by[kPeerMaxRanks];
 };
+static_assert(sizeof(PeerHeader) <= kPeerHeaderBytes, "exchange-buffer header too large");
 
 struct PeerSet {
     int nranks, rank;
@@ -48,12 +51,12 @@ __device__ __forceinline__ double* peer_contrib(const PeerSet& ps, int r, unsign
     return reinterpret_cast<double*>(ps.base[r] + kPeerHeaderBytes) + (epoch & 1ull) * n;
 }
 
-// Thread 0 of the CTA waits until `field` of every rank's header has reached `target`; returns false on timeout.
+// Thread 0 of the CTA waits until every rank has published `target`: its `ready` counter (read from the peer's buffer),
+// or its consumption of THIS rank's contributions (read from this rank's own header); returns false on timeout.
 __device__ __forceinline__ bool peer_wait_all(const PeerSet& ps, bool consumed_field, unsigned long long target) {
     const long long t0 = clock64();
     for (int r = 0; r < ps.nranks; r++) {
-        const PeerHeader* hd = peer_header(ps, r);
-        const unsigned long long* f = consumed_field ? &hd->consumed : &hd->ready;
+        const unsigned long long* f = consumed_field ? &peer_header(ps, ps.rank)->consumed_by[r] : &peer_header(ps, r)->ready;
         while (ld_acquire_sys(f) < target) {
             if (clock64() - t0 > kPeerSpinLimit) return false;
             __nanosleep(200);
@@ -137,7 +140,8 @@ __global__ void k_peer_sum(PeerSet ps, unsigned long long epoch, int nb, int nma
         if (atomicAdd(&me->ticket[1], 1u) == gridDim.x - 1) {
             me->ticket[1] = 0u;
             __threadfence_system();
-            st_release_sys(&me->consumed, epoch);
+            // tell every owner (this rank included) that its epoch-`epoch` contribution has been read
+            for (int r = 0; r < ps.nranks; r++) st_release_sys(&peer_header(ps, r)->consumed_by[ps.rank], epoch);
         }
     }
 }
