@@ -8,8 +8,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -20,6 +24,7 @@
 #include "kernels_grid.cuh"
 #include "kernels_hartree.cuh"
 #include "kernels_peer.cuh"
+#include "kernels_scf.cuh"
 #include "nccl_dyn.h"
 
 using namespace dfg;
@@ -66,10 +71,12 @@ struct DevBuf {
 
 }  // namespace
 
+struct dftgrid_group;
 struct dftgrid {
     int device = 0, rank = 0, nranks = 1;
     cudaStream_t stream = nullptr;
     bool built = false, have_density = false, have_potential = false, contract_valid = false, timed_iter = false;
+    int fock_valid = -1;  // contraction mode whose result d_fres holds for the current density, or -1
     long launches = 0;
 
     // host description
@@ -98,17 +105,23 @@ struct dftgrid {
     DevBuf<int> d_pass_rng;
 
     // device: per point
-    DevBuf<double> d_x, d_y, d_z, d_w, d_wb, d_rho, d_dxc, d_exw, d_V, d_Vown, d_dJ, d_phi;
+    DevBuf<double> d_x, d_y, d_z, d_w, d_wb, d_rho, d_dxc, d_exw, d_V, d_Vown, d_dJ, d_dF, d_phi;
     // device: per iteration
-    DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
-    DevBuf<int> d_pairs, d_cta_off, d_item_off, d_chunk_ids;
+    DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_qatom2, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
+    DevBuf<int> d_pairs, d_chunk_ids;
+    // stream-K schedules of the contraction: [0] two matrices (XC, J), [1] one matrix (fused Fock build)
+    struct DevSchedule {
+        DevBuf<ConSeg> segs;
+        DevBuf<int> cta_off, item_off;
+        int ctas = 1, nsegs = 1;
+    } sched[2];
+    DevBuf<double> d_fres;  // fused build: [F (nb^2) | per-shell sums of w V rho (natoms*nrad) | e_j, exc, nel, pad]
     DevBuf<double> d_rho_part;  // partial densities when a tile's slabs are split over several CTAs
     int rho_split = 1;
     size_t rho_part_stride = 0;
     int con_bc = 1;
     long n_active_chunks = 0;
-    DevBuf<ConSeg> d_segs;
-    int npairs = 0, nsplit = 1, con_ctas = 1, interp_chunks = 1;
+    int npairs = 0, interp_chunks = 1;
     DevBuf<double> d_Vpart;
     // binned interpolation (see kernels_hartree.cuh): pairs sorted by (source atom, spline interval) at build time
     bool binned = false;
@@ -125,18 +138,45 @@ struct dftgrid {
     NcclComm comm = nullptr;
     // peer-memory reduction of [J | XC] (kernels_peer.cuh)
     unsigned char* xbuf = nullptr;        // this rank's exchange buffer
-    size_t xbuf_bytes = 0;
+    size_t xbuf_bytes = 0, xslot = 0;
     PeerSet peers{};
     std::vector<void*> peer_mapped;       // cudaIpcOpenMemHandle results to close
-    bool peer_ready = false;
+    bool peer_ready = false, peer_used = false, peer_local = false;  // peer_local: single-process group (no IPC mappings)
     unsigned long long peer_epoch = 0;
 
     // CUDA graph of one whole iteration (single-GPU handles): the 15 launches of a small molecule's iteration are
     // launch-latency bound, one graph launch replaces them from the second call of dftgrid_iteration_device on
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
-    bool capturing = false, graph_failed = false;
-    long eager_iterations = 0, graph_launches_per_iter = 0;
+    struct IterGraph {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool failed = false;
+        long eager = 0, launches_per_iter = 0;
+        void reset() {
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            graph = nullptr;
+            exec = nullptr;
+            failed = false;
+            eager = 0;
+        }
+    } graphs[3];  // per contraction mode (kModePair, kModeFock, kModeFockJ)
+    bool capturing = false;
+
+    // single-process multi-GPU: a group handle holds no device state of its own, only its rank handles
+    dftgrid_group* group = nullptr;
+
+    // device-resident SCF algebra (kernels_scf.cuh): H, X, X^T, work matrices [np][np], purification state
+    struct ScfState {
+        bool ready = false;
+        int np = 0, nocc = 0;
+        long steps = 0;
+        double alpha = 0.5;
+        DevBuf<double> H, X, Xt, F, T1, Fp, D, D2, D3, lo, hi, diag, rows, eone;
+        DevBuf<PmState> pm;
+        PmState* h_pm = nullptr;  // pinned
+        double* h_out = nullptr;  // pinned [8]
+        cudaEvent_t ev[3]{};
+    } scf;
 
     // timing
     cudaEvent_t ev[16]{};
@@ -145,14 +185,17 @@ struct dftgrid {
     double t_ms[DFTGRID_T_COUNT]{};
 
     ~dftgrid() {
-        if (graph_exec) cudaGraphExecDestroy(graph_exec);
-        if (graph) cudaGraphDestroy(graph);
+        for (auto& G : graphs) G.reset();
         for (void* m : peer_mapped) cudaIpcCloseMemHandle(m);
         if (xbuf) cudaFree(xbuf);
         if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         for (auto& e : ev_sw)
+            if (e) cudaEventDestroy(e);
+        if (scf.h_pm) cudaFreeHost(scf.h_pm);
+        if (scf.h_out) cudaFreeHost(scf.h_out);
+        for (auto& e : scf.ev)
             if (e) cudaEventDestroy(e);
         if (h_P) cudaFreeHost(h_P);
         if (h_res) cudaFreeHost(h_res);
@@ -257,7 +300,7 @@ struct ContractSchedule {
 };
 
 // Pure host arithmetic (no device): also exported as dftgrid_debug_contract_schedule for the CPU test-suite.
-void compute_contract_schedule(int nbp, long nchunk, int nsm, ContractSchedule& S) {
+void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSchedule& S) {
     S = ContractSchedule();
     const int nt = (nbp + kTileM - 1) / kTileM;
     for (int i = 0; i < nt; i++)
@@ -266,8 +309,12 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, ContractSchedule& 
             S.pairs.push_back(j);
         }
     S.npairs = (int)S.pairs.size() / 2;
-    const int npairs = S.npairs, nitems = 2 * npairs;
+    const int npairs = S.npairs, nitems = nz * npairs;
     std::vector<double> cost(nitems);
+    static const char* nc = std::getenv("DFTGRID_NARROW_COST");  // developer sweeps of the cost model
+    static const char* dc = std::getenv("DFTGRID_DIAG_COST");
+    static const char* ec = std::getenv("DFTGRID_EDGE_DIAG_COST");
+    static const char* l2e = std::getenv("DFTGRID_L2_BLOCK_MB");
     double W1 = 0.0;  // cost of all items for one chunk
     for (int it = 0; it < nitems; it++) {
         const int ti = S.pairs[2 * (it % npairs)], tj = S.pairs[2 * (it % npairs) + 1];
@@ -275,9 +322,6 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, ContractSchedule& 
         // (H2O)64, (H2O)32 and C40H82: a 64-wide edge tile issues half the DMMAs but pays the same loads (10.5), a
         // diagonal tile issues 17 of 32 DMMAs per warp (11.5), the 64-wide diagonal tile 8 of 32 (6.5; under-estimating
         // it makes its CTA the straggler, 5 costs 14 %)
-        const char* nc = std::getenv("DFTGRID_NARROW_COST");
-        const char* dc = std::getenv("DFTGRID_DIAG_COST");
-        const char* ec = std::getenv("DFTGRID_EDGE_DIAG_COST");
         const bool narrow = std::min(kTileN, nbp - tj * kTileN) <= 64;
         const double c_narrow = nc ? std::atof(nc) : 10.5, c_diag = dc ? std::atof(dc) : 11.5, c_edge_diag = ec ? std::atof(ec) : 6.5;
         cost[it] = ti == tj ? (narrow ? c_edge_diag : c_diag) : (narrow ? c_narrow : 20.0);
@@ -289,7 +333,7 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, ContractSchedule& 
     {
         const double chunk_bytes = (double)kTileK * nbp * sizeof(double);
         double l2_mb = 120.0;
-        if (const char* e = std::getenv("DFTGRID_L2_BLOCK_MB")) l2_mb = std::atof(e);  // developer sweep; <= 0: one block
+        if (l2e) l2_mb = std::atof(l2e);  // developer sweep; <= 0: one block
         long bc = l2_mb > 0 ? (long)(l2_mb * 1e6 / chunk_bytes) : nchunk;
         bc = std::max<long>(bc, 64);
         if (bc >= nchunk) bc = std::max<long>(nchunk, 1);
@@ -345,19 +389,24 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, ContractSchedule& 
 
 void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
     cudaStream_t st = h->stream;
-    ContractSchedule S;
-    compute_contract_schedule(h->nbp, nchunk, nsm, S);
-    h->npairs = S.npairs;
-    h->con_bc = S.bc;
-    h->d_pairs.upload(S.pairs, st);
-    h->con_ctas = (int)S.cta_off.size() - 1;
-    h->nsplit = (int)S.segs.size();
-    h->d_segs.alloc(S.segs.size());
-    CK(cudaMemcpyAsync(h->d_segs.p, S.segs.data(), S.segs.size() * sizeof(ConSeg), cudaMemcpyHostToDevice, st));
-    h->d_cta_off.upload(S.cta_off, st);
-    h->d_item_off.upload(S.item_off, st);
-    h->d_partial.alloc((size_t)S.segs.size() * kTileM * kTileN);
-    CK(cudaStreamSynchronize(st));  // S goes out of scope
+    size_t max_segs = 0;
+    for (int k = 0; k < 2; k++) {
+        ContractSchedule S;
+        compute_contract_schedule(h->nbp, nchunk, nsm, k == 0 ? 2 : 1, S);
+        h->npairs = S.npairs;
+        h->con_bc = S.bc;
+        if (k == 0) h->d_pairs.upload(S.pairs, st);
+        dftgrid::DevSchedule& D = h->sched[k];
+        D.ctas = (int)S.cta_off.size() - 1;
+        D.nsegs = (int)S.segs.size();
+        D.segs.alloc(S.segs.size());
+        CK(cudaMemcpyAsync(D.segs.p, S.segs.data(), S.segs.size() * sizeof(ConSeg), cudaMemcpyHostToDevice, st));
+        D.cta_off.upload(S.cta_off, st);
+        D.item_off.upload(S.item_off, st);
+        max_segs = std::max(max_segs, S.segs.size());
+        CK(cudaStreamSynchronize(st));  // S goes out of scope
+    }
+    h->d_partial.alloc(max_segs * kTileM * kTileN);
 }
 
 // Lists of the 32-point chunks / 128-point tiles of Phi that hold any non-zero amplitude (k_chunk_flags), and the
@@ -539,6 +588,8 @@ void do_build(dftgrid* h) {
     h->d_V.alloc(nlp);
     h->d_Vown.alloc(nlp);
     h->d_dJ.alloc(nlp);
+    h->d_dF.alloc(nlp);
+    h->d_dF.zero(st);
     h->d_dxc.zero(st);
     h->d_dJ.zero(st);
     h->d_rho.zero(st);  // tiles of exact-zero amplitudes are skipped by k_rho_tma: their density stays 0
@@ -552,6 +603,8 @@ void do_build(dftgrid* h) {
     h->d_shell_raw.alloc((size_t)nshell);
     h->d_shell2.alloc((size_t)nshell * 2 + (size_t)nshell * g.nlm);  // [shell sums (2 per shell) | rho_lm] contiguous: one collective
     h->d_qatom.alloc(g.natoms);
+    h->d_qatom2.alloc(g.natoms);
+    h->d_fres.alloc((size_t)h->nbf * h->nbf + (size_t)nshell + 4);
     h->d_scalars.alloc(4);
     h->d_U_lm.alloc((size_t)nshell * g.nlm);
     h->d_work.alloc(std::max((size_t)(g.nrad + 2) * nsys, (size_t)2 * g.nrad * nsys));
@@ -567,7 +620,7 @@ void do_build(dftgrid* h) {
         h->interp_chunks = (int)std::max<long>(1, std::min<long>(chunks, std::min<long>(g.natoms, 32)));  // point-parallel fallback only
     }
     if (!h->h_P) CK(cudaMallocHost(&h->h_P, sizeof(double) * std::max<size_t>(1, (size_t)h->nbf * h->nbf)));
-    if (!h->h_res) CK(cudaMallocHost(&h->h_res, sizeof(double) * ((size_t)2 * h->nbf * h->nbf + 2)));
+    if (!h->h_res) CK(cudaMallocHost(&h->h_res, sizeof(double) * ((size_t)2 * h->nbf * h->nbf + 4)));
 
     CK(cudaFuncSetAttribute(k_phi, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(((size_t)kPhiPts * (kPhiCols + 1) + (size_t)kPhiMaxExp * kPhiPts) * sizeof(double))));
@@ -735,6 +788,7 @@ void run_density(dftgrid* h) {
     h->have_density = true;
     h->have_potential = false;
     h->contract_valid = false;
+    h->fock_valid = -1;
     h->timed_iter = false;
 }
 
@@ -810,37 +864,82 @@ void run_potential(dftgrid* h) {
     h->have_potential = true;
 }
 
-// [XC | J] = Phi^T diag(d) Phi, results laid out as res = [J (nb^2) | XC (nb^2) | exc | nel]
-void run_contract(dftgrid* h) {
+// Contraction modes: kModePair  [XC | J] = Phi^T diag(d) Phi as two matrices, res = [J (nb^2) | XC (nb^2) | exc | nel];
+//                    kModeFock  F_grid = 2J + XC as ONE contraction with the summed weight vector (half the DMMA work),
+//                    kModeFockJ F_grid = 2J only (the reference's first iteration: XC still zero, src/dft.cpp:219-226);
+//                    the two Fock modes write fres = [F (nb^2) | per-shell sums of w V rho | e_j | exc | nel].
+enum { kModePair = 0, kModeFock = 1, kModeFockJ = 2 };
+
+void run_contract(dftgrid* h, int mode) {
     cudaStream_t st = h->stream;
+    const GridShape& g = h->g;
     const size_t nb2 = (size_t)h->nbf * h->nbf;
+    const long nshell = (long)g.natoms * g.nrad;
+    const bool fock = mode != kModePair;
+    const dftgrid::DevSchedule& D = h->sched[fock ? 1 : 0];
+    const int nz = fock ? 1 : 2;
     record(h, 12);
-    k_contract_tma<<<h->con_ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p, h->d_pairs.p,
-                                                                          h->d_segs.p, h->d_cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc);
+    double* ejshell = h->d_fres.p + nb2;
+    if (fock) {
+        // summed weight vector and the per-shell sums of the E_J integrand (zero outside this rank's shells)
+        if (h->nranks > 1) CK(cudaMemsetAsync(ejshell, 0, (size_t)nshell * sizeof(double), st));
+        if (g.nloc > 0) {
+            k_fock_weights<<<(unsigned)((g.nloc + 255) / 256), 256, 0, st>>>(g.nloc, h->d_dJ.p, h->d_dxc.p, mode == kModeFock ? 1 : 0, h->d_dF.p);
+            k_shell_sum<<<(unsigned)((g.nshell_loc * 32 + 255) / 256), 256, 0, st>>>(g, h->d_dJ.p, h->d_rho.p, ejshell, 1, 0);
+            h->launches += 2;
+        }
+    }
+    if (h->peer_ready) {
+        k_peer_begin<<<1, 1, 0, st>>>(h->peers);
+        h->peer_epoch++;
+        h->peer_used = true;
+        h->launches++;
+    }
+    k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, fock ? h->d_dF.p : h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p, h->d_pairs.p,
+                                                                     D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc);
+    double* res = fock ? h->d_fres.p : h->d_res.p;
     if (h->peer_ready) {
         // split-K reduction straight into this rank's exchange buffer, then the cross-rank sum over peer memory
-        h->peer_epoch++;
-        k_contract_reduce_publish<<<dim3(h->npairs, 2, kReduceSplit), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp,
-                                                                     1.0, 0.5, h->peers, h->peer_epoch);
+        if (fock)
+            k_contract_reduce_publish<<<dim3(h->npairs, 1, kReduceSplit), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, D.item_off.p, h->npairs, h->nbf, h->nbp,
+                                                                                     1.0, 1.0, 0, 0, ejshell, (int)nshell, nb2, h->peers);
+        else  // res layout [J | XC]; item z = 0 is XC
+            k_contract_reduce_publish<<<dim3(h->npairs, 2, kReduceSplit), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, D.item_off.p, h->npairs, h->nbf, h->nbp,
+                                                                                     1.0, 0.5, nb2, 0, nullptr, 0, 2 * nb2, h->peers);
     } else {
-        k_contract_reduce<<<dim3(h->npairs, 2, kReduceSplit), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, h->d_item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 0.5,
-                                                             h->d_res.p + nb2, h->d_res.p);
+        if (fock)
+            k_contract_reduce<<<dim3(h->npairs, 1, kReduceSplit), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, D.item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 1.0,
+                                                                             res, res);
+        else
+            k_contract_reduce<<<dim3(h->npairs, 2, kReduceSplit), 256, 0, st>>>(h->d_partial.p, h->d_pairs.p, D.item_off.p, h->npairs, h->nbf, h->nbp, 1.0, 0.5,
+                                                                             res + nb2, res);
     }
     h->launches += 2;
-    // exc and nel come from the already-reduced shell sums (identical on every rank): appended after the reduced block
-    CK(cudaMemcpyAsync(h->d_res.p + 2 * nb2, h->d_scalars.p + 2, sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(h->d_res.p + 2 * nb2 + 1, h->d_scalars.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, st));
     record(h, 13);
     if (h->peer_ready) {
-        const size_t n = 2 * nb2;
+        const size_t n = nz * nb2 + (fock ? (size_t)nshell : 0);
         const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 296);
-        k_peer_sum<<<blocks, 256, 0, st>>>(h->peers, h->peer_epoch, h->nbf, 2, h->d_res.p);
+        k_peer_sum<<<blocks, 256, 0, st>>>(h->peers, h->nbf, nz, fock ? (int)nshell : 0, res);
         h->launches++;
     } else {
-        allreduce(h, h->d_res.p, 2 * nb2);
+        allreduce(h, res, nz * nb2 + (fock ? (size_t)nshell : 0));
+    }
+    // exc and nel come from the already-reduced shell sums (identical on every rank): appended after the reduced block
+    if (fock) {
+        k_fock_scalars<<<1, 256, 0, st>>>(g, ejshell, h->d_scalars.p, h->d_qatom2.p, h->d_fres.p + nb2 + nshell);
+        h->launches++;
+    } else {
+        CK(cudaMemcpyAsync(res + 2 * nb2, h->d_scalars.p + 2, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(res + 2 * nb2 + 1, h->d_scalars.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     record(h, 14);
-    h->contract_valid = h->have_potential;
+    if (fock) {
+        h->fock_valid = h->have_potential ? mode : -1;
+        h->contract_valid = false;
+    } else {
+        h->contract_valid = h->have_potential;
+        h->fock_valid = -1;
+    }
     h->timed_iter = h->have_potential;
 }
 
@@ -906,11 +1005,12 @@ int guarded(F&& f) {
 void use_device(dftgrid* h) { CK(cudaSetDevice(h->device)); }
 
 // After a stream synchronisation: a bounded spin-wait of the peer-memory reduction that gave up leaves a flag behind.
+// The flag is sticky on purpose: the epochs of the ranks are out of step from then on, the handle must be recreated.
 void check_peer_error(dftgrid* h) {
     if (!h->peer_ready) return;
     unsigned long long err = 0;
     CK(cudaMemcpy(&err, h->xbuf + offsetof(PeerHeader, error), sizeof err, cudaMemcpyDeviceToHost));
-    if (err) throw std::runtime_error("peer-memory reduction timed out waiting for another rank");
+    if (err) throw std::runtime_error("peer-memory reduction timed out waiting for another rank (the handle is unusable now: destroy and recreate it)");
 }
 
 template <typename T>
@@ -920,12 +1020,325 @@ void download(dftgrid* h, const DevBuf<T>& b, T* out, size_t count) {
     CK(cudaStreamSynchronize(h->stream));
 }
 
+// Rows [r0, r1) of an nb x nb device matrix into the caller's matrix: straight from the DMA engine when the caller's
+// buffer is page-locked, through the handle's pinned staging otherwise (`pending` remembers the memcpy still to do after
+// the stream has been synchronised).
+struct PendingCopy {
+    double* dst;
+    const double* src;
+    size_t bytes;
+};
+void download_rows(dftgrid* h, const double* dev, double* host, double* stage, int r0, int r1, std::vector<PendingCopy>& pending) {
+    if (!host || r1 <= r0) return;
+    const size_t off = (size_t)r0 * h->nbf, bytes = (size_t)(r1 - r0) * h->nbf * sizeof(double);
+    if (is_pinned_host(host)) {
+        CK(cudaMemcpyAsync(host + off, dev + off, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        CK(cudaMemcpyAsync(stage + off, dev + off, bytes, cudaMemcpyDeviceToHost, h->stream));
+        pending.push_back(PendingCopy{host + off, stage + off, bytes});
+    }
+}
+
+void require_density(dftgrid* h) {
+    if (!h->have_density) throw std::runtime_error("dftgrid_set_density has not been called");
+}
+
+// One whole iteration's kernels in the given contraction mode, eagerly the first time (every lazily sized buffer exists
+// afterwards), captured into a CUDA graph the second time and replayed from then on.  Multi-rank handles are captured
+// too: the peer-memory kernels read their epoch from device memory and NCCL collectives are capturable.
+void run_iteration_device(dftgrid* h, int mode) {
+    if (!h->built) throw std::runtime_error("dftgrid_build has not been called");
+    static const bool no_graph = std::getenv("DFTGRID_NO_GRAPH") != nullptr;  // developer A/B switch
+    dftgrid::IterGraph& G = h->graphs[mode];
+    const bool want_graph = !no_graph && !G.failed && mode != kModeFockJ;
+    auto mark = [&] {
+        h->have_density = h->have_potential = h->timed_iter = true;
+        h->contract_valid = mode == kModePair;
+        h->fock_valid = mode == kModePair ? -1 : mode;
+    };
+    if (want_graph && G.exec) {
+        CK(cudaGraphLaunch(G.exec, h->stream));
+        h->launches += G.launches_per_iter;
+        if (h->peer_ready) {
+            h->peer_epoch++;
+            h->peer_used = true;
+        }
+        mark();
+        return;
+    }
+    if (want_graph && G.eager >= 1) {
+        const long l0 = h->launches;
+        const unsigned long long e0 = h->peer_epoch;
+        bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            h->capturing = true;
+            try {
+                run_density(h);
+                run_potential(h);
+                run_contract(h, mode);
+            } catch (...) {
+                ok = false;
+            }
+            h->capturing = false;
+            cudaGraph_t gcap = nullptr;
+            if (cudaStreamEndCapture(h->stream, &gcap) != cudaSuccess || !gcap) ok = false;
+            if (ok && cudaGraphInstantiate(&G.exec, gcap, 0) != cudaSuccess) ok = false;
+            if (ok) {
+                G.graph = gcap;
+                G.launches_per_iter = h->launches - l0;
+            } else if (gcap) {
+                cudaGraphDestroy(gcap);
+            }
+        }
+        h->launches = l0;
+        h->peer_epoch = e0;  // nothing ran during the capture
+        if (!ok) {
+            cudaGetLastError();
+            G.exec = nullptr;
+            G.failed = true;  // stay on eager launches
+        } else {
+            CK(cudaGraphLaunch(G.exec, h->stream));
+            h->launches += G.launches_per_iter;
+            if (h->peer_ready) {
+                h->peer_epoch++;
+                h->peer_used = true;
+            }
+            mark();
+            return;
+        }
+    }
+    run_density(h);
+    run_potential(h);
+    run_contract(h, mode);
+    G.eager++;
+    CK(cudaGetLastError());
+}
+
+
+// ---- device-resident SCF step (kernels_scf.cuh) ----------------------------------------------------------------------
+template <bool SYM>
+void scf_gemm(dftgrid* h, const double* A, const double* B, double* C, const int* skip) {
+    const int np = h->scf.np, nt = np / kGemmTile;
+    if (SYM)
+        k_gemm_nn<true><<<nt * (nt + 1) / 2, kGemmThreads, kGemmSmemBytes, h->stream>>>(A, B, C, np, skip);
+    else
+        k_gemm_nn<false><<<dim3(nt, nt), kGemmThreads, kGemmSmemBytes, h->stream>>>(A, B, C, np, skip);
+    h->launches++;
+}
+
+void scf_init(dftgrid* h, const double* H, const double* X, int nocc, double alpha) {
+    if (!h->built) throw std::runtime_error("dftgrid_build has not been called");
+    if (nocc < 0 || nocc > h->nbf) throw std::runtime_error("dftgrid_scf_init: nocc out of range");
+    auto& S = h->scf;
+    cudaStream_t st = h->stream;
+    const int nb = h->nbf, np = round_up(nb, kGemmTile);
+    const size_t nb2 = (size_t)nb * nb, np2 = (size_t)np * np;
+    S.np = np;
+    S.nocc = nocc;
+    S.alpha = alpha;
+    S.steps = 0;
+    S.H.alloc(nb2);
+    for (DevBuf<double>* b : {&S.X, &S.Xt, &S.F, &S.T1, &S.Fp, &S.D, &S.D2, &S.D3}) b->alloc(np2);
+    for (DevBuf<double>* b : {&S.lo, &S.hi, &S.diag, &S.rows}) b->alloc(nb);
+    S.eone.alloc(1);
+    S.pm.alloc(1);
+    if (!S.h_pm) CK(cudaMallocHost(&S.h_pm, sizeof(PmState)));
+    if (!S.h_out) CK(cudaMallocHost(&S.h_out, 8 * sizeof(double)));
+    for (auto& e : S.ev)
+        if (!e) CK(cudaEventCreate(&e));
+    CK(cudaFuncSetAttribute(k_gemm_nn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(k_gemm_nn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+    // H and X arrive row-major nb x nb (H symmetric; X = U s^-1/2 is not): pad X, build X^T once
+    CK(cudaMemcpyAsync(S.H.p, H, nb2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.T1.p, X, nb2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const unsigned eb = (unsigned)((np2 + 255) / 256);
+    k_scf_pad_sum<<<eb, 256, 0, st>>>(S.T1.p, nullptr, nb, np, S.X.p);
+    k_scf_transpose<<<dim3(np / 32, np / 32), dim3(32, 8), 0, st>>>(S.X.p, np, S.Xt.p);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    S.ready = true;
+}
+
+// out[8] = e_one, e_j, exc, nelec, purification steps, idempotency residual |tr(D - D^2)|, algebra ms, grid ms
+void scf_step(dftgrid* h, int include_xc, double* out) {
+    auto& S = h->scf;
+    if (!S.ready) throw std::runtime_error("dftgrid_scf_init has not been called");
+    cudaStream_t st = h->stream;
+    const int nb = h->nbf, np = S.np;
+    const size_t nb2 = (size_t)nb * nb, np2 = (size_t)np * np;
+    const unsigned eb = (unsigned)((np2 + 255) / 256);
+    CK(cudaEventRecord(S.ev[0], st));
+    // F = H + F_grid of the previous step (none before the first density: core-Hamiltonian guess, src/dft.cpp:176-182)
+    k_scf_pad_sum<<<eb, 256, 0, st>>>(S.H.p, S.steps > 0 ? h->d_fres.p : nullptr, nb, np, S.F.p);
+    h->launches++;
+    scf_gemm<false>(h, S.F.p, S.X.p, S.T1.p, nullptr);   // T1 = F X
+    scf_gemm<true>(h, S.Xt.p, S.T1.p, S.Fp.p, nullptr);  // F' = X^T F X
+    int pm_iters = 0;
+    double pm_err = 0.0;
+    if (S.nocc >= nb || S.nocc == 0) {
+        if (S.nocc == 0)
+            CK(cudaMemsetAsync(S.D.p, 0, np2 * sizeof(double), st));
+        else
+            k_scf_identity<<<eb, 256, 0, st>>>(nb, np, S.D.p);
+        h->launches++;
+    } else {
+        k_pm_gershgorin<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, st>>>(S.Fp.p, nb, np, S.lo.p, S.hi.p, S.diag.p);
+        k_pm_setup<<<1, 256, 0, st>>>(S.lo.p, S.hi.p, S.diag.p, nb, S.nocc, S.pm.p);
+        k_pm_init<<<eb, 256, 0, st>>>(S.Fp.p, nb, np, S.pm.p, S.D.p);
+        h->launches += 3;
+        const int* skip = &S.pm.p->done;
+        const int kBatch = 8, kMaxIter = 128;
+        S.h_pm->done = 0;
+        for (int it = 0; it < kMaxIter && !S.h_pm->done; it += kBatch) {
+            for (int b = 0; b < kBatch; b++) {
+                scf_gemm<true>(h, S.D.p, S.D.p, S.D2.p, skip);
+                scf_gemm<true>(h, S.D.p, S.D2.p, S.D3.p, skip);
+                k_pm_coeff<<<1, 256, 0, st>>>(S.D.p, S.D2.p, S.D3.p, nb, np, S.pm.p);
+                k_pm_update<<<eb, 256, 0, st>>>(S.D.p, S.D2.p, S.D3.p, np, S.pm.p);
+                h->launches += 2;
+            }
+            CK(cudaMemcpyAsync(S.h_pm, S.pm.p, sizeof(PmState), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (S.h_pm->failed) throw std::runtime_error("density purification: F' is a multiple of the identity");
+        if (!S.h_pm->done)
+            throw std::runtime_error("density purification did not converge (no gap between the occupied and virtual orbitals?); "
+                                     "use the host eigen-solver (scf = host)");
+        pm_iters = S.h_pm->iters;
+        pm_err = S.h_pm->err;
+    }
+    scf_gemm<false>(h, S.X.p, S.D.p, S.T1.p, nullptr);   // T2 = X D'
+    scf_gemm<true>(h, S.T1.p, S.Xt.p, S.D2.p, nullptr);  // Pnew = X D' X^T
+    k_scf_mix<<<(unsigned)((nb2 + 255) / 256), 256, 0, st>>>(S.D2.p, nb, np, S.alpha, S.steps == 0 ? 1 : 0, h->d_Praw.p);
+    k_pad_P<<<(unsigned)((nb2 + 255) / 256), 256, 0, st>>>(h->d_Praw.p, h->d_P.p, nb, h->nbp);
+    k_scf_rowdot<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, st>>>(h->d_Praw.p, S.H.p, nb, S.rows.p);
+    k_scf_trace_finish<<<1, 256, 0, st>>>(S.rows.p, nb, 2.0, S.eone.p);
+    h->launches += 4;
+    CK(cudaEventRecord(S.ev[1], st));
+    run_iteration_device(h, include_xc ? kModeFock : kModeFockJ);
+    CK(cudaEventRecord(S.ev[2], st));
+    const size_t nshell = (size_t)h->g.natoms * h->g.nrad;
+    CK(cudaMemcpyAsync(S.h_out, S.eone.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(S.h_out + 1, h->d_fres.p + nb2 + nshell, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    check_peer_error(h);
+    S.steps++;
+    float ms_alg = 0.f, ms_grid = 0.f;
+    CK(cudaEventElapsedTime(&ms_alg, S.ev[0], S.ev[1]));
+    CK(cudaEventElapsedTime(&ms_grid, S.ev[1], S.ev[2]));
+    if (out) {
+        for (int i = 0; i < 4; i++) out[i] = S.h_out[i];
+        out[4] = pm_iters;
+        out[5] = pm_err;
+        out[6] = ms_alg;
+        out[7] = ms_grid;
+    }
+}
+
+// ---- single-process multi-GPU: a group handle owns one rank handle per device and one worker thread per rank; every
+// public entry point forwards to the rank handles on their threads and returns when all of them are done.
+struct Group {
+    std::vector<dftgrid*> subs;
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    std::function<int(dftgrid*, int)> job;
+    unsigned long gen = 0;
+    int pending = 0;
+    bool stop = false;
+    std::vector<int> rc;
+    std::vector<std::string> err;
+
+    void worker(int r) {
+        cudaSetDevice(subs[r]->device);
+        unsigned long seen = 0;
+        for (;;) {
+            std::function<int(dftgrid*, int)> f;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_job.wait(lk, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen;
+                f = job;
+            }
+            int code = 0;
+            try {
+                code = f(subs[r], r);
+            } catch (const std::exception& e) {
+                g_error = e.what();
+                code = 1;
+            } catch (...) {
+                g_error = "unknown error";
+                code = 2;
+            }
+            {
+                std::lock_guard<std::mutex> lk(m);
+                rc[r] = code;
+                if (code) err[r] = g_error;
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    void start() {
+        rc.assign(subs.size(), 0);
+        err.assign(subs.size(), std::string());
+        for (size_t r = 0; r < subs.size(); r++) threads.emplace_back([this, r] { worker((int)r); });
+    }
+    int run(std::function<int(dftgrid*, int)> f) {
+        std::unique_lock<std::mutex> lk(m);
+        job = std::move(f);
+        pending = (int)subs.size();
+        gen++;
+        cv_job.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+        for (size_t r = 0; r < subs.size(); r++)
+            if (rc[r]) {
+                g_error = "rank " + std::to_string(r) + ": " + err[r];
+                return rc[r];
+            }
+        return 0;
+    }
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv_job.notify_all();
+        for (auto& t : threads) t.join();
+        threads.clear();
+    }
+};
+
+inline void row_slice(int nb, int r, int n, int* r0, int* r1) {
+    *r0 = (int)((long)nb * r / n);
+    *r1 = (int)((long)nb * (r + 1) / n);
+}
+
+void alloc_xbuf(dftgrid* h) {
+    if (h->xbuf) return;
+    const size_t nb2 = (size_t)h->nbf * h->nbf;
+    const size_t nshell = (size_t)h->natoms * h->prm.radial_points;
+    h->xslot = std::max(2 * nb2, nb2 + nshell);
+    h->xbuf_bytes = kPeerHeaderBytes + 2 * h->xslot * sizeof(double);
+    CK(cudaMalloc(&h->xbuf, h->xbuf_bytes));
+    CK(cudaMemset(h->xbuf, 0, h->xbuf_bytes));
+    const unsigned long long lim = kPeerDefaultTimeoutNs;
+    CK(cudaMemcpy(h->xbuf + offsetof(PeerHeader, spin_limit_ns), &lim, sizeof lim, cudaMemcpyHostToDevice));
+}
+
 }  // namespace
+
+struct dftgrid_group : Group {};
 
 extern "C" {
 
 const char* dftgrid_last_error(void) { return g_error.c_str(); }
-int dftgrid_abi_version(void) { return 1; }
+int dftgrid_abi_version(void) { return 2; }
+
+#define GROUP_FORWARD(h, expr)                                                        \
+    if ((h)->group) return (h)->group->run([&](dftgrid* s, int r) -> int { (void)r; return (expr); })
 
 int dftgrid_create(dftgrid_t** out, const dftgrid_system* sys, const dftgrid_params* prm, int device, int rank, int nranks) {
     return guarded([&] {
@@ -961,14 +1374,116 @@ int dftgrid_create(dftgrid_t** out, const dftgrid_system* sys, const dftgrid_par
     });
 }
 
+int dftgrid_create_multi(dftgrid_t** out, const dftgrid_system* sys, const dftgrid_params* prm, int ngpus, const int* devices) {
+    if (!out) {
+        g_error = "null argument";
+        return 1;
+    }
+    *out = nullptr;
+    if (ngpus == 1) return dftgrid_create(out, sys, prm, devices ? devices[0] : 0, 0, 1);
+    std::unique_ptr<dftgrid> gh(new dftgrid());
+    int rc = guarded([&] {
+        if (ngpus < 1 || ngpus > kPeerMaxRanks) throw std::runtime_error("ngpus must be 1..16");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw std::runtime_error(std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+        if (ngpus > ndev && !devices) throw std::runtime_error("ngpus exceeds the number of visible CUDA devices (" + std::to_string(ndev) + ")");
+        gh->group = new dftgrid_group();
+        gh->nranks = ngpus;
+        for (int r = 0; r < ngpus; r++) {
+            dftgrid_t* s = nullptr;
+            if (dftgrid_create(&s, sys, prm, devices ? devices[r] : r, r, ngpus) != 0) throw std::runtime_error(g_error);
+            gh->group->subs.push_back(s);
+        }
+        gh->nbf = gh->group->subs[0]->nbf;
+        gh->natoms = gh->group->subs[0]->natoms;
+        gh->prm = *prm;
+        gh->device = gh->group->subs[0]->device;
+        // the small per-shell sums go through NCCL (one communicator per device, created in one call)
+        if (!nccl_api().load() || !nccl_api().CommInitAll) throw std::runtime_error("cannot load libnccl.so.2 (needed for ngpus > 1)");
+        std::vector<NcclComm> comms(ngpus);
+        std::vector<int> devs(ngpus);
+        for (int r = 0; r < ngpus; r++) devs[r] = gh->group->subs[r]->device;
+        int nrc = nccl_api().CommInitAll(comms.data(), ngpus, devs.data());
+        if (nrc != 0) throw std::runtime_error(std::string("ncclCommInitAll: ") + nccl_api().GetErrorString(nrc));
+        for (int r = 0; r < ngpus; r++) gh->group->subs[r]->comm = comms[r];
+        gh->group->start();
+        // peer-memory path for the [J | XC] / F sum when every pair of devices has a P2P route
+        bool p2p = true;
+        for (int a = 0; a < ngpus && p2p; a++)
+            for (int b = 0; b < ngpus && p2p; b++) {
+                int can = 1;
+                if (a != b && (cudaDeviceCanAccessPeer(&can, devs[a], devs[b]) != cudaSuccess || !can)) p2p = false;
+            }
+        static const bool no_peer = std::getenv("DFTGRID_NO_PEER") != nullptr;  // developer A/B switch
+        if (p2p && !no_peer) {
+            int prc = gh->group->run([&](dftgrid* s, int r) -> int {
+                return guarded([&] {
+                    use_device(s);
+                    for (int b = 0; b < ngpus; b++)
+                        if (b != r) {
+                            cudaError_t pe = cudaDeviceEnablePeerAccess(devs[b], 0);
+                            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+                            cudaGetLastError();
+                        }
+                    alloc_xbuf(s);
+                });
+            });
+            if (prc != 0) throw std::runtime_error(g_error);
+            PeerSet ps{};
+            ps.nranks = ngpus;
+            ps.slot = gh->group->subs[0]->xslot;
+            for (int r = 0; r < ngpus; r++) ps.base[r] = gh->group->subs[r]->xbuf;
+            for (int r = 0; r < ngpus; r++) {
+                dftgrid* s = gh->group->subs[r];
+                s->peers = ps;
+                s->peers.rank = r;
+                s->peer_ready = true;
+                s->peer_local = true;
+            }
+        }
+    });
+    if (rc != 0) {
+        const std::string keep = g_error;
+        dftgrid_destroy(gh.release());
+        g_error = keep;
+        return rc;
+    }
+    *out = gh.release();
+    return 0;
+}
+
+int dftgrid_ngpus(const dftgrid_t* h) { return h->group ? (int)h->group->subs.size() : 1; }
+
 void dftgrid_destroy(dftgrid_t* h) {
     if (!h) return;
+    if (h->group) {
+        // every rank's stream is drained before any exchange buffer is freed: nobody is still reading a peer
+        if (!h->group->threads.empty()) {
+            h->group->run([](dftgrid* s, int) -> int {
+                cudaSetDevice(s->device);
+                cudaStreamSynchronize(s->stream);
+                return 0;
+            });
+            h->group->shutdown();
+        }
+        for (dftgrid* s : h->group->subs) dftgrid_destroy(s);
+        h->group->subs.clear();
+        delete h->group;
+        h->group = nullptr;
+        delete h;
+        return;
+    }
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    if (h->peer_ready && h->peer_epoch > 0) {
-        // another rank may still be summing this rank's exchange buffer (its k_peer_sum of the last epoch): wait, bounded,
-        // until every peer has written consumed_by[peer] >= the last epoch into THIS rank's header, then free it
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->peer_used && !h->peer_local && h->peer_epoch > 0) {
+        // one process per GPU: another rank may still be summing this rank's exchange buffer (its k_peer_sum of the last
+        // epoch).  Wait, bounded, until every peer has written consumed_by[peer] >= the last epoch into THIS rank's header;
+        // if a peer never gets there the buffer is leaked rather than freed under its feet (freeing an exported
+        // allocation another process still has mapped is undefined behaviour).
         const auto t0 = std::chrono::steady_clock::now();
+        bool all = true;
         for (int r = 0; r < h->peers.nranks; r++) {
             if (r == h->rank) continue;
             unsigned long long consumed = 0;
@@ -978,8 +1493,10 @@ void dftgrid_destroy(dftgrid_t* h) {
                     cudaGetLastError();
                     break;
                 }
-            } while (consumed < h->peer_epoch && std::chrono::steady_clock::now() - t0 < std::chrono::seconds(5));
+            } while (consumed < h->peer_epoch && std::chrono::steady_clock::now() - t0 < std::chrono::seconds(30));
+            if (consumed < h->peer_epoch) all = false;
         }
+        if (!all) h->xbuf = nullptr;  // leaked on purpose
     }
     delete h;
 }
@@ -1006,6 +1523,7 @@ int dftgrid_comm_unique_id(void* id128) {
 
 int dftgrid_comm_init(dftgrid_t* h, const void* id128) {
     return guarded([&] {
+        if (h->group) throw std::runtime_error("a multi-GPU handle wires its own communicator");
         if (!nccl_api().load()) throw std::runtime_error("cannot load libnccl.so.2");
         use_device(h);
         NcclUniqueId id;
@@ -1017,16 +1535,12 @@ int dftgrid_comm_init(dftgrid_t* h, const void* id128) {
 
 int dftgrid_peer_export(dftgrid_t* h, void* handle64) {
     return guarded([&] {
+        if (h->group) throw std::runtime_error("a multi-GPU handle wires its own peer mappings");
         use_device(h);
         if (!handle64) throw std::runtime_error("null argument");
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
         if (h->nranks < 2 || h->nranks > kPeerMaxRanks) throw std::runtime_error("peer reduction needs 2..16 ranks");
-        if (!h->xbuf) {
-            const size_t nb2 = (size_t)h->nbf * h->nbf;
-            h->xbuf_bytes = kPeerHeaderBytes + 2 * (2 * nb2) * sizeof(double);
-            CK(cudaMalloc(&h->xbuf, h->xbuf_bytes));
-            CK(cudaMemset(h->xbuf, 0, h->xbuf_bytes));
-        }
+        alloc_xbuf(h);
         cudaIpcMemHandle_t hd;
         CK(cudaIpcGetMemHandle(&hd, h->xbuf));
         std::memcpy(handle64, &hd, sizeof hd);
@@ -1035,6 +1549,7 @@ int dftgrid_peer_export(dftgrid_t* h, void* handle64) {
 
 int dftgrid_peer_connect(dftgrid_t* h, const void* handles) {
     return guarded([&] {
+        if (h->group) throw std::runtime_error("a multi-GPU handle wires its own peer mappings");
         use_device(h);
         if (!handles) throw std::runtime_error("null argument");
         if (!h->xbuf) throw std::runtime_error("dftgrid_peer_export has not been called");
@@ -1042,6 +1557,7 @@ int dftgrid_peer_connect(dftgrid_t* h, const void* handles) {
         PeerSet ps{};
         ps.nranks = h->nranks;
         ps.rank = h->rank;
+        ps.slot = h->xslot;
         for (int r = 0; r < h->nranks; r++) {
             if (r == h->rank) {
                 ps.base[r] = h->xbuf;
@@ -1065,19 +1581,48 @@ int dftgrid_peer_connect(dftgrid_t* h, const void* handles) {
     });
 }
 
-int dftgrid_peer_active(const dftgrid_t* h) { return h->peer_ready ? 1 : 0; }
+int dftgrid_peer_active(const dftgrid_t* h) {
+    if (h->group) return h->group->subs[0]->peer_ready ? 1 : 0;
+    return h->peer_ready ? 1 : 0;
+}
 
 int dftgrid_peer_disable(dftgrid_t* h) {
+    GROUP_FORWARD(h, dftgrid_peer_disable(s));
     return guarded([&] {
         use_device(h);
         CK(cudaStreamSynchronize(h->stream));
         h->peer_ready = false;  // back to ncclAllReduce; the mappings stay open until the handle is destroyed
+        for (auto& G : h->graphs) G.reset();  // captured graphs hold the peer kernels
+    });
+}
+
+int dftgrid_peer_set_timeout(dftgrid_t* h, double seconds) {
+    GROUP_FORWARD(h, dftgrid_peer_set_timeout(s, seconds));
+    return guarded([&] {
+        use_device(h);
+        if (!h->xbuf) throw std::runtime_error("no peer exchange buffer on this handle");
+        if (!(seconds > 0.0)) throw std::runtime_error("timeout must be positive");
+        const unsigned long long lim = (unsigned long long)(seconds * 1e9);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(h->xbuf + offsetof(PeerHeader, spin_limit_ns), &lim, sizeof lim, cudaMemcpyHostToDevice));
     });
 }
 
 int dftgrid_build(dftgrid_t* h) {
+    if (h->group) {
+        int rc = h->group->run([&](dftgrid* s, int) -> int { return dftgrid_build(s); });
+        if (rc == 0) {
+            h->g = h->group->subs[0]->g;
+            h->g.shell0 = 0;
+            h->g.nshell_loc = (long)h->g.natoms * h->g.nrad;
+            h->g.nloc = h->g.npts;
+            h->built = true;
+        }
+        return rc;
+    }
     return guarded([&] {
         use_device(h);
+        if (h->built) throw std::runtime_error("dftgrid_build has already been called on this handle");
         do_build(h);
     });
 }
@@ -1089,6 +1634,7 @@ int dftgrid_nbf(const dftgrid_t* h) { return h->nbf; }
 int dftgrid_nlm(const dftgrid_t* h) { return h->g.nlm; }
 
 int dftgrid_upload_density(dftgrid_t* h, const double* P) {
+    GROUP_FORWARD(h, dftgrid_upload_density(s, P));
     return guarded([&] {
         use_device(h);
         if (upload_P(h, P)) CK(cudaStreamSynchronize(h->stream));  // the caller may reuse P as soon as this returns
@@ -1096,6 +1642,7 @@ int dftgrid_upload_density(dftgrid_t* h, const double* P) {
 }
 
 int dftgrid_set_density(dftgrid_t* h, const double* P) {
+    GROUP_FORWARD(h, dftgrid_set_density(s, P));
     return guarded([&] {
         use_device(h);
         upload_P(h, P);
@@ -1105,44 +1652,72 @@ int dftgrid_set_density(dftgrid_t* h, const double* P) {
     });
 }
 
-int dftgrid_hartree_J(dftgrid_t* h, double* J) {
+// rows [r0, r1) of J only (every rank of a group holds the whole matrix; each one delivers its slice)
+static int hartree_J_rows(dftgrid_t* h, double* J, int r0, int r1) {
     return guarded([&] {
         use_device(h);
-        if (!h->have_density) throw std::runtime_error("dftgrid_set_density has not been called");
-        const size_t nb2 = (size_t)h->nbf * h->nbf;
+        require_density(h);
         run_potential(h);
-        run_contract(h);
+        run_contract(h, kModePair);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h->h_res, h->d_res.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        std::vector<PendingCopy> pend;
+        download_rows(h, h->d_res.p, J, h->h_res, r0, r1, pend);
         CK(cudaStreamSynchronize(h->stream));
         check_peer_error(h);
-        std::memcpy(J, h->h_res, nb2 * sizeof(double));
+        for (auto& c : pend) std::memcpy(c.dst, c.src, c.bytes);
+    });
+}
+
+int dftgrid_hartree_J(dftgrid_t* h, double* J) {
+    if (h->group) {
+        const int n = (int)h->group->subs.size();
+        return h->group->run([&](dftgrid* s, int r) -> int {
+            int r0, r1;
+            row_slice(s->nbf, r, n, &r0, &r1);
+            return hartree_J_rows(s, J, r0, r1);
+        });
+    }
+    return hartree_J_rows(h, J, 0, h->nbf);
+}
+
+static int xc_rows(dftgrid_t* h, double* XC, double* exc, int r0, int r1) {
+    return guarded([&] {
+        use_device(h);
+        require_density(h);
+        const size_t nb2 = (size_t)h->nbf * h->nbf;
+        if (!h->contract_valid) {
+            // XC asked for before J: the J half of the two-matrix contraction still needs a defined weight vector
+            if (!h->have_potential) h->d_dJ.zero(h->stream);
+            run_contract(h, kModePair);
+        }
+        CK(cudaGetLastError());
+        std::vector<PendingCopy> pend;
+        download_rows(h, h->d_res.p + nb2, XC, h->h_res + nb2, r0, r1, pend);
+        CK(cudaMemcpyAsync(h->h_res + 2 * nb2, h->d_res.p + 2 * nb2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        check_peer_error(h);
+        for (auto& c : pend) std::memcpy(c.dst, c.src, c.bytes);
+        if (exc) *exc = h->h_res[2 * nb2];
     });
 }
 
 int dftgrid_xc(dftgrid_t* h, double* XC, double* exc) {
-    return guarded([&] {
-        use_device(h);
-        if (!h->have_density) throw std::runtime_error("dftgrid_set_density has not been called");
-        const size_t nb2 = (size_t)h->nbf * h->nbf;
-        if (!h->contract_valid) {
-            // XC asked for before J: the J half of the fused contraction still needs a defined weight vector
-            if (!h->have_potential) h->d_dJ.zero(h->stream);
-            run_contract(h);
-        }
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h->h_res, h->d_res.p + nb2, (nb2 + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        check_peer_error(h);
-        if (XC) std::memcpy(XC, h->h_res, nb2 * sizeof(double));
-        if (exc) *exc = h->h_res[nb2];
-    });
+    if (h->group) {
+        const int n = (int)h->group->subs.size();
+        return h->group->run([&](dftgrid* s, int r) -> int {
+            int r0, r1;
+            row_slice(s->nbf, r, n, &r0, &r1);
+            return xc_rows(s, XC, r == 0 ? exc : nullptr, r0, r1);
+        });
+    }
+    return xc_rows(h, XC, exc, 0, h->nbf);
 }
 
 int dftgrid_electron_count(dftgrid_t* h, double* nelec) {
+    if (h->group) return dftgrid_electron_count(h->group->subs[0], nelec);
     return guarded([&] {
         use_device(h);
-        if (!h->have_density) throw std::runtime_error("dftgrid_set_density has not been called");
+        require_density(h);
         CK(cudaMemcpyAsync(h->h_res, h->d_scalars.p + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         *nelec = h->h_res[0];
@@ -1150,103 +1725,142 @@ int dftgrid_electron_count(dftgrid_t* h, double* nelec) {
 }
 
 int dftgrid_iteration_device(dftgrid_t* h) {
+    GROUP_FORWARD(h, dftgrid_iteration_device(s));
     return guarded([&] {
         use_device(h);
-        if (!h->built) throw std::runtime_error("dftgrid_build has not been called");
-        static const bool no_graph = std::getenv("DFTGRID_NO_GRAPH") != nullptr;  // developer A/B switch
-        const bool want_graph = h->nranks == 1 && !no_graph && !h->graph_failed;
-        if (want_graph && h->graph_exec) {
-            CK(cudaGraphLaunch(h->graph_exec, h->stream));
-            h->launches += h->graph_launches_per_iter;
-            h->have_density = h->have_potential = h->contract_valid = h->timed_iter = true;
-            return;
-        }
-        if (want_graph && h->eager_iterations >= 1) {
-            // the first iteration ran eagerly (every lazily sized buffer exists now): capture the second one
-            const long l0 = h->launches;
-            bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-            if (ok) {
-                h->capturing = true;
-                try {
-                    run_density(h);
-                    run_potential(h);
-                    run_contract(h);
-                } catch (...) {
-                    ok = false;
-                }
-                h->capturing = false;
-                cudaGraph_t gcap = nullptr;
-                if (cudaStreamEndCapture(h->stream, &gcap) != cudaSuccess || !gcap) ok = false;
-                if (ok && cudaGraphInstantiate(&h->graph_exec, gcap, 0) != cudaSuccess) ok = false;
-                if (ok) {
-                    h->graph = gcap;
-                    h->graph_launches_per_iter = h->launches - l0;
-                    h->launches = l0;
-                } else if (gcap) {
-                    cudaGraphDestroy(gcap);
-                }
-            }
-            if (!ok) {
-                cudaGetLastError();
-                h->graph_exec = nullptr;
-                h->graph_failed = true;  // stay on eager launches
-                h->launches = l0;
-            } else {
-                CK(cudaGraphLaunch(h->graph_exec, h->stream));
-                h->launches += h->graph_launches_per_iter;
-                h->have_density = h->have_potential = h->contract_valid = h->timed_iter = true;
-                return;
-            }
-        }
-        run_density(h);
-        run_potential(h);
-        run_contract(h);
-        h->eager_iterations++;
-        CK(cudaGetLastError());
+        run_iteration_device(h, kModePair);
     });
 }
 
-int dftgrid_download_results(dftgrid_t* h, double* J, double* XC, double* exc, double* nelec) {
+int dftgrid_fock_device(dftgrid_t* h, int include_xc) {
+    GROUP_FORWARD(h, dftgrid_fock_device(s, include_xc));
     return guarded([&] {
         use_device(h);
+        run_iteration_device(h, include_xc ? kModeFock : kModeFockJ);
+    });
+}
+
+static int download_results_rows(dftgrid_t* h, double* J, double* XC, double* exc, double* nelec, int r0, int r1) {
+    return guarded([&] {
+        use_device(h);
+        if (!h->contract_valid) throw std::runtime_error("no [J | XC] result on the device for the current density");
         const size_t nb2 = (size_t)h->nbf * h->nbf;
-        // page-locked caller buffers receive their matrix straight from the DMA engine; others go through h_res
-        const bool dj = J && is_pinned_host(J), dx = XC && is_pinned_host(XC);
-        if (dj) CK(cudaMemcpyAsync(J, h->d_res.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (J && !dj) CK(cudaMemcpyAsync(h->h_res, h->d_res.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (dx) CK(cudaMemcpyAsync(XC, h->d_res.p + nb2, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (XC && !dx) CK(cudaMemcpyAsync(h->h_res + nb2, h->d_res.p + nb2, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        std::vector<PendingCopy> pend;
+        download_rows(h, h->d_res.p, J, h->h_res, r0, r1, pend);
+        download_rows(h, h->d_res.p + nb2, XC, h->h_res + nb2, r0, r1, pend);
         CK(cudaMemcpyAsync(h->h_res + 2 * nb2, h->d_res.p + 2 * nb2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         check_peer_error(h);
-        if (J && !dj) std::memcpy(J, h->h_res, nb2 * sizeof(double));
-        if (XC && !dx) std::memcpy(XC, h->h_res + nb2, nb2 * sizeof(double));
+        for (auto& c : pend) std::memcpy(c.dst, c.src, c.bytes);
         if (exc) *exc = h->h_res[2 * nb2];
         if (nelec) *nelec = h->h_res[2 * nb2 + 1];
     });
 }
 
+int dftgrid_download_results(dftgrid_t* h, double* J, double* XC, double* exc, double* nelec) {
+    if (h->group) {
+        const int n = (int)h->group->subs.size();
+        return h->group->run([&](dftgrid* s, int r) -> int {
+            int r0, r1;
+            row_slice(s->nbf, r, n, &r0, &r1);
+            return download_results_rows(s, J, XC, r == 0 ? exc : nullptr, r == 0 ? nelec : nullptr, r0, r1);
+        });
+    }
+    return download_results_rows(h, J, XC, exc, nelec, 0, h->nbf);
+}
+
+static int download_fock_rows(dftgrid_t* h, double* F, double* e_j, double* exc, double* nelec, int r0, int r1) {
+    return guarded([&] {
+        use_device(h);
+        if (h->fock_valid < 0) throw std::runtime_error("no fused Fock result on the device for the current density");
+        const size_t nb2 = (size_t)h->nbf * h->nbf;
+        const size_t nshell = (size_t)h->g.natoms * h->g.nrad;
+        std::vector<PendingCopy> pend;
+        download_rows(h, h->d_fres.p, F, h->h_res, r0, r1, pend);
+        CK(cudaMemcpyAsync(h->h_res + 2 * nb2, h->d_fres.p + nb2 + nshell, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        check_peer_error(h);
+        for (auto& c : pend) std::memcpy(c.dst, c.src, c.bytes);
+        if (e_j) *e_j = h->h_res[2 * nb2];
+        if (exc) *exc = h->h_res[2 * nb2 + 1];
+        if (nelec) *nelec = h->h_res[2 * nb2 + 2];
+    });
+}
+
+int dftgrid_download_fock(dftgrid_t* h, double* F, double* e_j, double* exc, double* nelec) {
+    if (h->group) {
+        const int n = (int)h->group->subs.size();
+        return h->group->run([&](dftgrid* s, int r) -> int {
+            int r0, r1;
+            row_slice(s->nbf, r, n, &r0, &r1);
+            return download_fock_rows(s, F, r == 0 ? e_j : nullptr, r == 0 ? exc : nullptr, r == 0 ? nelec : nullptr, r0, r1);
+        });
+    }
+    return download_fock_rows(h, F, e_j, exc, nelec, 0, h->nbf);
+}
+
 int dftgrid_iteration(dftgrid_t* h, const double* P, double* J, double* XC, double* exc, double* nelec) {
+    if (h->group) {
+        const int n = (int)h->group->subs.size();
+        return h->group->run([&](dftgrid* s, int r) -> int {
+            int r0, r1;
+            row_slice(s->nbf, r, n, &r0, &r1);
+            int rc = guarded([&] {
+                use_device(s);
+                upload_P(s, P);
+                run_iteration_device(s, kModePair);
+            });
+            if (rc) return rc;
+            return download_results_rows(s, J, XC, r == 0 ? exc : nullptr, r == 0 ? nelec : nullptr, r0, r1);
+        });
+    }
     // P is consumed by the time the download below has synchronised the stream, so a pinned P is read in place
     int rc = guarded([&] {
         use_device(h);
         upload_P(h, P);
+        run_iteration_device(h, kModePair);
     });
     if (rc) return rc;
-    rc = dftgrid_iteration_device(h);
+    return download_results_rows(h, J, XC, exc, nelec, 0, h->nbf);
+}
+
+int dftgrid_fock(dftgrid_t* h, const double* P, int include_xc, double* F, double* e_j, double* exc, double* nelec) {
+    const int mode = include_xc ? kModeFock : kModeFockJ;
+    if (h->group) {
+        const int n = (int)h->group->subs.size();
+        return h->group->run([&](dftgrid* s, int r) -> int {
+            int r0, r1;
+            row_slice(s->nbf, r, n, &r0, &r1);
+            int rc = guarded([&] {
+                use_device(s);
+                upload_P(s, P);
+                run_iteration_device(s, mode);
+            });
+            if (rc) return rc;
+            return download_fock_rows(s, F, r == 0 ? e_j : nullptr, r == 0 ? exc : nullptr, r == 0 ? nelec : nullptr, r0, r1);
+        });
+    }
+    int rc = guarded([&] {
+        use_device(h);
+        upload_P(h, P);
+        run_iteration_device(h, mode);
+    });
     if (rc) return rc;
-    return dftgrid_download_results(h, J, XC, exc, nelec);
+    return download_fock_rows(h, F, e_j, exc, nelec, 0, h->nbf);
 }
 
 int dftgrid_synchronize(dftgrid_t* h) {
+    GROUP_FORWARD(h, dftgrid_synchronize(s));
     return guarded([&] {
         use_device(h);
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaGetLastError());
+        check_peer_error(h);
     });
 }
 
 int dftgrid_get_positions(dftgrid_t* h, double* xyz) {
+    GROUP_FORWARD(h, dftgrid_get_positions(s, xyz + 3 * dftgrid_point_offset(s)));
     return guarded([&] {
         const size_t n = (size_t)h->g.nloc;
         std::vector<double> x(n), y(n), z(n);
@@ -1260,20 +1874,35 @@ int dftgrid_get_positions(dftgrid_t* h, double* xyz) {
         }
     });
 }
-int dftgrid_get_weights(dftgrid_t* h, double* w) { return guarded([&] { download(h, h->d_w, w, (size_t)h->g.nloc); }); }
-int dftgrid_get_becke_weights(dftgrid_t* h, double* wb) { return guarded([&] { download(h, h->d_wb, wb, (size_t)h->g.nloc); }); }
-int dftgrid_get_densities(dftgrid_t* h, double* rho) { return guarded([&] { download(h, h->d_rho, rho, (size_t)h->g.nloc); }); }
-int dftgrid_get_potential(dftgrid_t* h, double* V) { return guarded([&] { download(h, h->d_V, V, (size_t)h->g.nloc); }); }
+int dftgrid_get_weights(dftgrid_t* h, double* w) {
+    GROUP_FORWARD(h, dftgrid_get_weights(s, w + dftgrid_point_offset(s)));
+    return guarded([&] { download(h, h->d_w, w, (size_t)h->g.nloc); });
+}
+int dftgrid_get_becke_weights(dftgrid_t* h, double* wb) {
+    GROUP_FORWARD(h, dftgrid_get_becke_weights(s, wb + dftgrid_point_offset(s)));
+    return guarded([&] { download(h, h->d_wb, wb, (size_t)h->g.nloc); });
+}
+int dftgrid_get_densities(dftgrid_t* h, double* rho) {
+    GROUP_FORWARD(h, dftgrid_get_densities(s, rho + dftgrid_point_offset(s)));
+    return guarded([&] { download(h, h->d_rho, rho, (size_t)h->g.nloc); });
+}
+int dftgrid_get_potential(dftgrid_t* h, double* V) {
+    GROUP_FORWARD(h, dftgrid_get_potential(s, V + dftgrid_point_offset(s)));
+    return guarded([&] { download(h, h->d_V, V, (size_t)h->g.nloc); });
+}
 int dftgrid_get_amplitudes(dftgrid_t* h, double* phi) {
+    GROUP_FORWARD(h, dftgrid_get_amplitudes(s, phi + (size_t)dftgrid_point_offset(s) * s->nbf));
     return guarded([&] {
         use_device(h);
         const size_t n = (size_t)h->g.nloc;
+        if (n == 0) return;
         CK(cudaMemcpy2DAsync(phi, (size_t)h->nbf * sizeof(double), h->d_phi.p, (size_t)h->nbp * sizeof(double),
                              (size_t)h->nbf * sizeof(double), n, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     });
 }
 int dftgrid_get_rho_lm(dftgrid_t* h, double* out) {
+    if (h->group) return dftgrid_get_rho_lm(h->group->subs[0], out);
     return guarded([&] {
         use_device(h);
         const size_t nshell = (size_t)h->g.natoms * h->g.nrad;
@@ -1282,10 +1911,23 @@ int dftgrid_get_rho_lm(dftgrid_t* h, double* out) {
     });
 }
 int dftgrid_get_U_lm(dftgrid_t* h, double* out) {
+    if (h->group) return dftgrid_get_U_lm(h->group->subs[0], out);
     return guarded([&] { download(h, h->d_U_lm, out, (size_t)h->g.natoms * h->g.nrad * h->g.nlm); });
 }
 
 int dftgrid_last_timings(dftgrid_t* h, double* out, int n) {
+    if (h->group) {
+        // per phase, the slowest rank
+        const int cnt = std::min(n, (int)DFTGRID_T_COUNT);
+        std::vector<std::vector<double>> t(h->group->subs.size(), std::vector<double>(DFTGRID_T_COUNT, 0.0));
+        int rc = h->group->run([&](dftgrid* s, int r) -> int { return dftgrid_last_timings(s, t[r].data(), DFTGRID_T_COUNT); });
+        if (rc) return rc;
+        for (int i = 0; i < cnt; i++) {
+            out[i] = 0.0;
+            for (auto& v : t) out[i] = std::max(out[i], v[i]);
+        }
+        return 0;
+    }
     return guarded([&] {
         use_device(h);
         CK(cudaStreamSynchronize(h->stream));
@@ -1295,6 +1937,7 @@ int dftgrid_last_timings(dftgrid_t* h, double* out, int n) {
 }
 
 int dftgrid_timer_start(dftgrid_t* h) {
+    GROUP_FORWARD(h, dftgrid_timer_start(s));
     return guarded([&] {
         use_device(h);
         CK(cudaEventRecord(h->ev_sw[0], h->stream));
@@ -1302,6 +1945,13 @@ int dftgrid_timer_start(dftgrid_t* h) {
 }
 
 int dftgrid_timer_stop(dftgrid_t* h, double* ms) {
+    if (h->group) {
+        std::vector<double> t(h->group->subs.size(), 0.0);
+        int rc = h->group->run([&](dftgrid* s, int r) -> int { return dftgrid_timer_stop(s, &t[r]); });
+        if (rc) return rc;
+        *ms = *std::max_element(t.begin(), t.end());
+        return 0;
+    }
     return guarded([&] {
         use_device(h);
         CK(cudaEventRecord(h->ev_sw[1], h->stream));
@@ -1312,15 +1962,22 @@ int dftgrid_timer_stop(dftgrid_t* h, double* ms) {
     });
 }
 
-long dftgrid_launch_count(const dftgrid_t* h) { return h->launches; }
+long dftgrid_launch_count(const dftgrid_t* h) {
+    if (h->group) {
+        long n = 0;
+        for (const dftgrid* s : h->group->subs) n += s->launches;
+        return n;
+    }
+    return h->launches;
+}
 
-int dftgrid_debug_contract_schedule(int nbp, long nchunk, int nsm, int max_segs, int* segs_out, int* cta_off_out, int* nctas, int* nsegs,
-                                    int* block_chunks) {
+int dftgrid_debug_contract_schedule_nz(int nbp, long nchunk, int nsm, int nz, int max_segs, int* segs_out, int* cta_off_out, int* nctas, int* nsegs,
+                                       int* block_chunks) {
     return guarded([&] {
-        if (nbp <= 0 || nbp % kNbAlign != 0 || nchunk < 0 || nsm <= 0 || !segs_out || !cta_off_out || !nctas || !nsegs || !block_chunks)
+        if (nbp <= 0 || nbp % kNbAlign != 0 || nchunk < 0 || nsm <= 0 || nz < 1 || nz > 2 || !segs_out || !cta_off_out || !nctas || !nsegs || !block_chunks)
             throw std::runtime_error("dftgrid_debug_contract_schedule: bad arguments");
         ContractSchedule S;
-        compute_contract_schedule(nbp, nchunk, nsm, S);
+        compute_contract_schedule(nbp, nchunk, nsm, nz, S);
         if ((int)S.segs.size() > max_segs) throw std::runtime_error("dftgrid_debug_contract_schedule: max_segs too small");
         for (size_t i = 0; i < S.segs.size(); i++) {
             segs_out[4 * i + 0] = S.segs[i].z;
@@ -1333,6 +1990,62 @@ int dftgrid_debug_contract_schedule(int nbp, long nchunk, int nsm, int max_segs,
         *nsegs = (int)S.segs.size();
         *block_chunks = S.bc;
     });
+}
+
+int dftgrid_debug_contract_schedule(int nbp, long nchunk, int nsm, int max_segs, int* segs_out, int* cta_off_out, int* nctas, int* nsegs,
+                                    int* block_chunks) {
+    return dftgrid_debug_contract_schedule_nz(nbp, nchunk, nsm, 2, max_segs, segs_out, cta_off_out, nctas, nsegs, block_chunks);
+}
+
+int dftgrid_scf_init(dftgrid_t* h, const double* H, const double* X, int nocc, double alpha) {
+    GROUP_FORWARD(h, dftgrid_scf_init(s, H, X, nocc, alpha));
+    return guarded([&] {
+        use_device(h);
+        scf_init(h, H, X, nocc, alpha);
+    });
+}
+
+int dftgrid_scf_step(dftgrid_t* h, int include_xc, double* out8) {
+    if (h->group) {
+        // every device repeats the (deterministic) algebra on its own copy: no traffic, identical bits
+        return h->group->run([&](dftgrid* s, int r) -> int {
+            double tmp[8];
+            return dftgrid_scf_step(s, include_xc, r == 0 ? out8 : tmp);
+        });
+    }
+    return guarded([&] {
+        use_device(h);
+        scf_step(h, include_xc, out8);
+    });
+}
+
+int dftgrid_scf_get_matrix(dftgrid_t* h, int which, double* out) {
+    if (h->group) return dftgrid_scf_get_matrix(h->group->subs[0], which, out);
+    return guarded([&] {
+        use_device(h);
+        if (!h->scf.ready) throw std::runtime_error("dftgrid_scf_init has not been called");
+        const int nb = h->nbf, np = h->scf.np;
+        const size_t nb2 = (size_t)nb * nb;
+        if (which == DFTGRID_SCF_P) {
+            CK(cudaMemcpyAsync(out, h->d_Praw.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        } else if (which == DFTGRID_SCF_FGRID) {
+            CK(cudaMemcpyAsync(out, h->d_fres.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        } else if (which == DFTGRID_SCF_FPRIME || which == DFTGRID_SCF_DPRIME) {
+            const double* src = which == DFTGRID_SCF_FPRIME ? h->scf.Fp.p : h->scf.D.p;
+            CK(cudaMemcpy2DAsync(out, (size_t)nb * sizeof(double), src, (size_t)np * sizeof(double), (size_t)nb * sizeof(double), nb,
+                                 cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            throw std::runtime_error("dftgrid_scf_get_matrix: unknown matrix id");
+        }
+        CK(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dftgrid_host_register(void* p, size_t bytes) {
+    return guarded([&] { CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable)); });
+}
+int dftgrid_host_unregister(void* p) {
+    return guarded([&] { CK(cudaHostUnregister(p)); });
 }
 
 }  // extern "C"

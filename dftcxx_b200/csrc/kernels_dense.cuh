@@ -59,7 +59,10 @@ constexpr int kTileM = 128;
 constexpr int kTileN = 128;
 constexpr int kTileK = 32;
 constexpr int kLdK = kTileK + 4;    // 36
-constexpr int kLdN = kTileN + 8;    // 136
+#ifndef DFG_LDN_PAD
+#define DFG_LDN_PAD 8
+#endif
+constexpr int kLdN = kTileN + DFG_LDN_PAD;    // 136 (pad 8) or 132 (pad 4)
 constexpr int kStages = 3;
 
 // flags[c] = 1 when any amplitude of the 32 rows of chunk c is non-zero.  Far from every nucleus exp(-alpha r^2)

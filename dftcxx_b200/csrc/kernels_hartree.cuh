@@ -54,6 +54,35 @@ __global__ void k_totals(GridShape g, const double* __restrict__ shellsum, int s
     }
 }
 
+// Fused Fock build: one weight vector for F_grid = 2J + XC = Phi^T diag(w (V + v_xc)) Phi (src/dft.cpp:334 only ever
+// uses the sum H + 2J + XC).  dJ = w V, dxc = w v_xc; without_xc reproduces the reference's first iteration, whose F holds
+// J(P0) but XC = 0 (src/dft.cpp:219-226).
+__global__ void k_fock_weights(long nloc, const double* __restrict__ dJ, const double* __restrict__ dxc, int include_xc, double* __restrict__ dF) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nloc) return;
+    dF[p] = include_xc ? dJ[p] + dxc[p] : dJ[p];
+}
+
+// E_J = 2 tr(P J) (src/dft.cpp:443) without forming J: 2 sum_ij P_ij J_ij = sum_p w_p V_p (rho_raw,p / 2), rho_raw the
+// density of P BEFORE the rescale = rho / scale.  shellsum[s] = sum over the shell's points of (w V) * rho (k_shell_sum),
+// summed per atom in radial order, then over the atoms in order (sharding independent).  out = [e_j, exc, nel].
+__global__ void k_fock_scalars(GridShape g, const double* __restrict__ shellsum, const double* __restrict__ scalars, double* __restrict__ q_tmp,
+                               double* __restrict__ out) {
+    for (int a = threadIdx.x; a < g.natoms; a += blockDim.x) {
+        double q = 0.0;
+        for (int i = 0; i < g.nrad; i++) q += shellsum[(long)a * g.nrad + i];
+        q_tmp[a] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int a = 0; a < g.natoms; a++) tot += q_tmp[a];
+        out[0] = 0.5 * tot / scalars[0];
+        out[1] = scalars[2];
+        out[2] = scalars[1];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // rho *= scale, then Slater-Xalpha exchange + VWN5 correlation for a closed shell (rho_a = rho_b = rho/2):
 // src/functionals.cpp:24-63 (exchange), 65-114 with zeta = 0 => g = 0 < tol, paramagnetic branch only, 116-150.

@@ -17,6 +17,7 @@ struct NcclApi {
     void* lib = nullptr;
     int (*GetUniqueId)(NcclUniqueId*) = nullptr;
     int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+    int (*CommInitAll)(NcclComm*, int, const int*) = nullptr;  // single-process multi-GPU handles
     int (*CommDestroy)(NcclComm) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int /*dtype*/, int /*op*/, NcclComm, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -32,6 +33,7 @@ struct NcclApi {
         if (!lib) return false;
         GetUniqueId = (int (*)(NcclUniqueId*))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+        CommInitAll = (int (*)(NcclComm*, int, const int*))dlsym(lib, "ncclCommInitAll");
         CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
         AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllReduce");
         GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");

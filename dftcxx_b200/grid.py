@@ -10,7 +10,7 @@ import numpy as np
 from .molecule import LEBEDEV_COUNTS
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdftgrid.so")
+LIB_PATH = os.environ.get("DFTGRID_LIB") or os.path.join(HERE, "libdftgrid.so")  # DFTGRID_LIB: developer A/B builds
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -41,6 +41,15 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.dftgrid_last_error.restype = C.c_char_p
     L.dftgrid_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_System), C.POINTER(_Params), C.c_int, C.c_int, C.c_int]
+    L.dftgrid_create_multi.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_System), C.POINTER(_Params), C.c_int, _ip]
+    L.dftgrid_ngpus.argtypes = [C.c_void_p]
+    L.dftgrid_peer_set_timeout.argtypes = [C.c_void_p, C.c_double]
+    L.dftgrid_fock.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp, _dp]
+    L.dftgrid_fock_device.argtypes = [C.c_void_p, C.c_int]
+    L.dftgrid_download_fock.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    L.dftgrid_scf_init.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double]
+    L.dftgrid_scf_step.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.dftgrid_scf_get_matrix.argtypes = [C.c_void_p, C.c_int, _dp]
     L.dftgrid_destroy.argtypes = [C.c_void_p]
     L.dftgrid_destroy.restype = None
     L.dftgrid_comm_unique_id.argtypes = [C.c_void_p]
@@ -98,7 +107,9 @@ class MolecularGrid:
     """B200 grid engine handle.  mol: anything with Z, xyz, bf_nprim, bf_center, alpha, coeff, norm, lmn arrays
     (dftcxx_b200.molecule.Molecule or the dict oracle/refpy.Ref.system() returns)."""
 
-    def __init__(self, mol, device=0, rank=0, nranks=1):
+    def __init__(self, mol, device=0, rank=0, nranks=1, ngpus=1, devices=None):
+        """ngpus > 1: ONE handle driving that many devices of this box from this process (dftgrid_create_multi);
+        rank/nranks: one process per GPU (dftgrid_create + comm_id / connect_peers)."""
         get = (lambda k: mol[k]) if isinstance(mol, dict) else (lambda k: getattr(mol, k))
         self._keep = dict(
             Z=np.ascontiguousarray(get("Z"), dtype=np.int32), xyz=np.ascontiguousarray(get("xyz"), dtype=np.float64),
@@ -110,6 +121,9 @@ class MolecularGrid:
         self.nbf = len(self._keep["bf_nprim"])
         self.nprim = len(self._keep["alpha"])
         self.device, self.rank, self.nranks = device, rank, nranks
+        self.ngpus, self.devices = int(ngpus), devices
+        if self.ngpus > 1 and nranks > 1:
+            raise GridError("ngpus > 1 (single process) and nranks > 1 (one process per GPU) are exclusive")
         self.h = None
         self.radial_points = self.lebedev_order = self.lmax = None
 
@@ -127,7 +141,11 @@ class MolecularGrid:
                        self.nprim, _ptr(k["alpha"]), _ptr(k["coeff"]), _ptr(k["norm"]), _ptr(k["lmn"], _ip))
         prm = _Params(self.radial_points, self.lebedev_order, self.lmax)
         h = C.c_void_p()
-        self._ck(lib().dftgrid_create(C.byref(h), C.byref(sysd), C.byref(prm), self.device, self.rank, self.nranks))
+        if self.ngpus > 1:
+            devs = None if self.devices is None else _ptr(np.ascontiguousarray(self.devices, dtype=np.int32), _ip)
+            self._ck(lib().dftgrid_create_multi(C.byref(h), C.byref(sysd), C.byref(prm), self.ngpus, devs))
+        else:
+            self._ck(lib().dftgrid_create(C.byref(h), C.byref(sysd), C.byref(prm), self.device, self.rank, self.nranks))
         self.close()
         self.h = h
         try:
@@ -224,6 +242,45 @@ class MolecularGrid:
         self._ck(lib().dftgrid_iteration(self.h, _ptr(self._mat(P)), _ptr(J), _ptr(XC), C.cast(C.byref(exc), _dp),
                                          C.cast(C.byref(nel), _dp)))
         return J, XC, exc.value, nel.value
+
+    def fock(self, P, include_xc=True, out=None):
+        """Fused Fock contribution (dftgrid_fock) -> (F_grid = 2J + XC, E_J, E_xc, N_el); out = caller-owned F array."""
+        F = np.empty((self.nbf, self.nbf)) if out is None else out
+        if F.dtype != np.float64 or F.shape != (self.nbf, self.nbf) or not F.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous float64 of shape (nbf, nbf)")
+        ej, exc, nel = C.c_double(), C.c_double(), C.c_double()
+        self._ck(lib().dftgrid_fock(self.h, _ptr(self._mat(P)), 1 if include_xc else 0, _ptr(F), C.cast(C.byref(ej), _dp),
+                                    C.cast(C.byref(exc), _dp), C.cast(C.byref(nel), _dp)))
+        return F, ej.value, exc.value, nel.value
+
+    def fock_device(self, include_xc=True):
+        self._ck(lib().dftgrid_fock_device(self.h, 1 if include_xc else 0))
+
+    def download_fock(self):
+        F = np.zeros((self.nbf, self.nbf))
+        ej, exc, nel = C.c_double(), C.c_double(), C.c_double()
+        self._ck(lib().dftgrid_download_fock(self.h, _ptr(F), C.cast(C.byref(ej), _dp), C.cast(C.byref(exc), _dp), C.cast(C.byref(nel), _dp)))
+        return F, ej.value, exc.value, nel.value
+
+    # -- device-resident SCF algebra (dftgrid_scf_*) -------------------------------------------------------
+    def scf_init(self, H, X, nocc, alpha=0.5):
+        """H: core Hamiltonian, X: orthogonalisation matrix U s^-1/2 (both nbf x nbf; X[i, j] = row i, column j)."""
+        self._ck(lib().dftgrid_scf_init(self.h, _ptr(self._mat(H)), _ptr(self._mat(X)), int(nocc), float(alpha)))
+
+    def scf_step(self, include_xc=True):
+        """One SCF loop body on the device -> dict(e_one, e_j, exc, nel, purification_steps, idempotency, ms_algebra, ms_grid)."""
+        o = np.zeros(8)
+        self._ck(lib().dftgrid_scf_step(self.h, 1 if include_xc else 0, _ptr(o)))
+        return dict(e_one=o[0], e_j=o[1], exc=o[2], nel=o[3], purification_steps=int(o[4]), idempotency=o[5], ms_algebra=o[6], ms_grid=o[7])
+
+    def scf_matrix(self, which):
+        """which: 'P' (mixed density matrix), 'F_grid', 'F_prime' (X^T F X), 'D_prime' (purified projector)."""
+        out = np.zeros((self.nbf, self.nbf))
+        self._ck(lib().dftgrid_scf_get_matrix(self.h, {"P": 0, "F_grid": 1, "F_prime": 2, "D_prime": 3}[which], _ptr(out)))
+        return out
+
+    def peer_active(self):
+        return lib().dftgrid_peer_active(self.h) == 1
 
     # -- device-resident path (benchmarks) ---------------------------------------------------------------
     def upload_density(self, P):

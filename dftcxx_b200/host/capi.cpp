@@ -16,9 +16,13 @@ const char* dfthost_last_error() { return g_err.c_str(); }
 // energies: [max_iter][6] = et, exc, e_one, e_j, nelec_grid, ms ; returns the number of iterations run, < 0 on error.
 // fixed_iterations > 0 runs exactly that many loop bodies (comparison at equal iteration index), otherwise the
 // reference's stopping rule (|dE| <= 1e-4 and >= 3 iterations) applies.
-int dfthost_scf(const char* infile, int device, int fixed_iterations, int max_iter, double* energies, double* enuc) {
+// ngpus: devices driven by the one process; scf_mode: 0 device-resident algebra, 1 host eigen-solver + fused Fock call,
+// 2 host eigen-solver + the reference's four grid calls (J and XC separately); -1 for either = the input file's keys.
+// Pout (optional, nb x nb): the final density matrix.
+int dfthost_scf2(const char* infile, int device, int ngpus, int scf_mode, int fixed_iterations, int max_iter, double* energies, double* enuc,
+                 double* Pout) {
     try {
-        dftcxx::DFT dft(infile, device, false);
+        dftcxx::DFT dft(infile, device, false, ngpus, scf_mode);
         if (fixed_iterations > 0)
             for (int i = 0; i < fixed_iterations && i < max_iter; i++) dft.scf_step();
         else
@@ -36,11 +40,19 @@ int dfthost_scf(const char* infile, int device, int fixed_iterations, int max_it
             e[5] = r.ms;
         }
         if (enuc) *enuc = dft.nuclear_repulsion();
+        if (Pout) {
+            const dftcxx::Mat P = dft.density_matrix();
+            std::memcpy(Pout, P.data(), sizeof(double) * P.rows() * P.cols());
+        }
         return n;
     } catch (const std::exception& e) {
         g_err = e.what();
         return -1;
     }
+}
+
+int dfthost_scf(const char* infile, int device, int fixed_iterations, int max_iter, double* energies, double* enuc) {
+    return dfthost_scf2(infile, device, -1, -1, fixed_iterations, max_iter, energies, enuc, nullptr);
 }
 
 // host-only: S, T, V (nb x nb each) for an input file; no GPU needed.  Returns nb or < 0.

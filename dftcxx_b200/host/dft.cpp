@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <stdexcept>
 
@@ -11,10 +12,18 @@ namespace dftcxx {
 using clk = std::chrono::system_clock;
 static long ms_since(const clk::time_point& t0) { return (long)std::chrono::duration_cast<std::chrono::milliseconds>(clk::now() - t0).count(); }
 
-DFT::DFT(const std::string& filename, int device_, bool verbose_) : verbose(verbose_), device(device_) {
+DFT::DFT(const std::string& filename, int device_, bool verbose_, int ngpus_, int scf_mode_)
+    : ngpus_opt(ngpus_), scf_mode_opt(scf_mode_), verbose(verbose_), device(device_) {
     settings = std::make_shared<Settings>(filename);
     mol = std::make_shared<Molecule>(filename, settings, verbose);
     add_molecule();
+}
+
+DFT::~DFT() {
+    if (pinned) {
+        dftgrid_host_unregister(P.data());
+        dftgrid_host_unregister(Fg.data());
+    }
 }
 
 void DFT::add_molecule() {
@@ -22,7 +31,9 @@ void DFT::add_molecule() {
     if (settings->get_hartree_evaluation_method() == Settings::TWO_ELECTRON_INTEGRALS)
         throw std::runtime_error("hartree_evaluation = two_electron_integrals is outside this build's scope "
                                  "(the GPU engine implements the becke_grid path); remove the key or set becke_grid");
-    molgrid.reset(new MolecularGrid(mol, device, verbose));
+    scf_mode = scf_mode_opt >= 0 ? (unsigned)scf_mode_opt : settings->get_scf_mode();
+    const int ngpus = ngpus_opt >= 1 ? ngpus_opt : (int)settings->get_gpus();
+    molgrid.reset(new MolecularGrid(mol, device, verbose, ngpus));
     molgrid->set_grid_parameters(settings->get_radial_points(), settings->get_lebedev_order(), settings->get_lmax());
     molgrid->create_grid();
     cgfs = mol->get_cgfs();
@@ -43,6 +54,11 @@ void DFT::construct_matrices() {
     J = Mat(n, n);
     XC = Mat(n, n);
     P = Mat(n, n);
+    Fg = Mat(n, n);
+    if (scf_mode == Settings::SCF_HOST_FUSED) {
+        // P and F_grid cross PCIe every iteration: page-lock them once so the engine DMAs in place
+        pinned = dftgrid_host_register(P.data(), sizeof(double) * n * n) == 0 && dftgrid_host_register(Fg.data(), sizeof(double) * n * n) == 0;
+    }
 #pragma omp parallel for schedule(dynamic)
     for (unsigned int i = 0; i < n; i++)
         for (unsigned int j = i; j < n; j++) {
@@ -58,6 +74,18 @@ void DFT::construct_matrices() {
         for (unsigned int j = 0; j < n; j++) H(i, j) = T(i, j) + V(i, j);
     calculate_nuclear_repulsion();
     calculate_transformation_matrix();
+    if (scf_mode == Settings::SCF_DEVICE) {
+        // H and X go to the device once; from here on P, F and the whole SCF algebra live in HBM
+        molgrid->scf_init(H, X, nelec / 2, 0.50);
+        double o[8];
+        molgrid->scf_step(false, o);  // core-Hamiltonian guess, then J(P0) only (XC stays zero until the first iteration)
+        single_electron_energy = o[0];
+        electronic_repulsion = o[1];
+        nelec_grid = o[3];
+        et = single_electron_energy + electronic_repulsion + enuc + exc;  // exc == 0 here, as in the reference
+        is_first = false;
+        return;
+    }
     calculate_density_matrix();              // core-Hamiltonian guess: J = XC = 0 here
     calculate_electronic_repulsion_matrix();
     calculate_energy();                      // exc is still zero at this point (the reference reads it uninitialised)
@@ -91,8 +119,9 @@ void DFT::calculate_density_matrix() {
     const double alpha = 0.50;
     const unsigned int n = mol->get_nr_bfs();
     Mat F(n, n);
+    const bool fused = scf_mode == Settings::SCF_HOST_FUSED;
     for (unsigned int i = 0; i < n; i++)
-        for (unsigned int j = 0; j < n; j++) F(i, j) = H(i, j) + 2.0 * J(i, j) + XC(i, j);
+        for (unsigned int j = 0; j < n; j++) F(i, j) = fused ? H(i, j) + Fg(i, j) : H(i, j) + 2.0 * J(i, j) + XC(i, j);
     const Mat Fp = matmul(matmul(Xp, F), X);
     std::vector<double> eps;
     Mat Cc;
@@ -114,27 +143,79 @@ void DFT::calculate_density_matrix() {
         for (unsigned int i = 0; i < n; i++)
             for (unsigned int j = 0; j < n; j++) P(i, j) = (1.0 - alpha) * Pnew(i, j) + alpha * P(i, j);
     }
+    if (fused) return;  // the fused Fock call of this iteration uploads P and builds the density itself
     molgrid->set_density(P);
     molgrid->correct_densities();
 }
 
-void DFT::calculate_electronic_repulsion_matrix() { J = molgrid->calculate_hartree_potential(); }
+void DFT::calculate_electronic_repulsion_matrix() {
+    if (scf_mode == Settings::SCF_HOST_FUSED) {
+        // construct_matrices: F_grid = 2 J(P0), XC not yet in F (src/dft.cpp:219-226); E_J = 2 tr(P J) comes back with it
+        double exc_unused = 0.0;
+        molgrid->fock(P, false, Fg, electronic_repulsion, exc_unused, nelec_grid);
+        return;
+    }
+    J = molgrid->calculate_hartree_potential();
+}
 
 void DFT::calculate_exchange_correlation_matrix() { XC = molgrid->calculate_exchange_correlation(exc); }
 
 void DFT::calculate_energy() {
     single_electron_energy = 2.0 * trace_of_product(P, H);
-    electronic_repulsion = 2.0 * trace_of_product(P, J);
+    if (scf_mode == Settings::SCF_HOST_SEPARATE) electronic_repulsion = 2.0 * trace_of_product(P, J);
     et = single_electron_energy + electronic_repulsion + enuc + exc;
 }
 
 double DFT::scf_step() {
     const auto t0 = clk::now();
-    calculate_density_matrix();
-    calculate_electronic_repulsion_matrix();
-    calculate_exchange_correlation_matrix();
-    calculate_energy();
-    records.push_back(ScfRecord{et, exc, single_electron_energy, electronic_repulsion, molgrid->calculate_density(), (double)ms_since(t0)});
+    ScfRecord rec{};
+    if (scf_mode == Settings::SCF_DEVICE) {
+        // the whole loop body (src/dft.cpp:100-103) on the device: one call, eight doubles back
+        double o[8];
+        bool ok = true;
+        try {
+            molgrid->scf_step(true, o);
+        } catch (const std::runtime_error& e) {
+            if (std::string(e.what()).find("purification") == std::string::npos) throw;
+            // no gap at the Fermi level: the projector is not defined by F' alone; continue on the host eigen-solver
+            // (which picks the nelec/2 lowest eigenvectors like the reference) from the device's current P and F_grid
+            if (verbose) std::cout << "note: " << e.what() << std::endl;
+            P = molgrid->scf_matrix(DFTGRID_SCF_P);
+            Fg = molgrid->scf_matrix(DFTGRID_SCF_FGRID);
+            scf_mode = Settings::SCF_HOST_FUSED;
+            ok = false;
+        }
+        if (ok) {
+            single_electron_energy = o[0];
+            electronic_repulsion = o[1];
+            exc = o[2];
+            nelec_grid = o[3];
+            et = single_electron_energy + electronic_repulsion + enuc + exc;
+            rec.purification_steps = (int)o[4];
+            rec.ms_algebra = o[6];
+            rec.ms_grid = o[7];
+        }
+    }
+    if (scf_mode == Settings::SCF_DEVICE) {
+        // done above
+    } else if (scf_mode == Settings::SCF_HOST_FUSED) {
+        calculate_density_matrix();
+        molgrid->fock(P, true, Fg, electronic_repulsion, exc, nelec_grid);
+        calculate_energy();
+    } else {
+        calculate_density_matrix();
+        calculate_electronic_repulsion_matrix();
+        calculate_exchange_correlation_matrix();
+        calculate_energy();
+        nelec_grid = molgrid->calculate_density();
+    }
+    rec.et = et;
+    rec.exc = exc;
+    rec.e_one = single_electron_energy;
+    rec.e_j = electronic_repulsion;
+    rec.nelec_grid = nelec_grid;
+    rec.ms = (double)ms_since(t0);
+    records.push_back(rec);
     return et;
 }
 
@@ -153,6 +234,7 @@ void DFT::scf(unsigned int max_iterations, double threshold) {
         const ScfRecord& r = records.back();
         if (verbose) {
             std::printf("%3u    %9.7f    %4.2f (%3u) \n", iteration, r.et, r.nelec_grid, nelec);
+            if (scf_mode == Settings::SCF_DEVICE && std::getenv("DFTCXX_TIMINGS")) std::printf("\tdevice: algebra %.2f ms (%d purification steps), grid %.2f ms\n", r.ms_algebra, r.purification_steps, r.ms_grid);
             std::printf("\tE_XC \t= %9.7f\n\tE_NUC \t= %9.7f\n\tE_ONE \t= %9.7f\n\tE_J \t= %9.7f\n\tt \t=%9ld ms\n", r.exc, enuc, r.e_one, r.e_j, (long)r.ms);
             std::cout << "----------------------------------------" << std::endl;
         }

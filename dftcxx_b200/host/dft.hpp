@@ -16,11 +16,15 @@ namespace dftcxx {
 
 struct ScfRecord {  // one line of the SCF table
     double et, exc, e_one, e_j, nelec_grid, ms;
+    double ms_algebra = 0.0, ms_grid = 0.0;  // device times of the two halves of the iteration (scf = device)
+    int purification_steps = 0;
 };
 
 class DFT {
 public:
-    explicit DFT(const std::string& filename, int device = 0, bool verbose = true);
+    // ngpus / scf_mode < 0: taken from the input file's `gpus` / `scf` / `fock` keys (Settings)
+    explicit DFT(const std::string& filename, int device = 0, bool verbose = true, int ngpus = -1, int scf_mode = -1);
+    ~DFT();
     void scf(unsigned int max_iterations = 100, double threshold = 1e-4);
 
     const std::vector<ScfRecord>& history() const { return records; }
@@ -28,7 +32,7 @@ public:
     const Mat& core_hamiltonian() const { return H; }
     const Mat& kinetic_matrix() const { return T; }
     const Mat& nuclear_matrix() const { return V; }
-    const Mat& density_matrix() const { return P; }
+    Mat density_matrix() const { return scf_mode == Settings::SCF_DEVICE ? molgrid->scf_matrix(DFTGRID_SCF_P) : P; }
     const Mat& coulomb_matrix() const { return J; }
     const Mat& xc_matrix() const { return XC; }
     double nuclear_repulsion() const { return enuc; }
@@ -52,7 +56,11 @@ private:
     std::unique_ptr<MolecularGrid> molgrid;
     Integrator integrator;
     const std::vector<CGF>* cgfs = nullptr;
-    Mat S, T, V, H, X, Xp, C, P, J, XC;
+    Mat S, T, V, H, X, Xp, C, P, J, XC, Fg;  // Fg: the grid's Fock contribution 2J + XC (fused modes)
+    int ngpus_opt, scf_mode_opt;
+    unsigned int scf_mode = Settings::SCF_DEVICE;
+    double nelec_grid = 0.0;
+    bool pinned = false;
     unsigned int nelec = 0;
     double exc = 0.0, enuc = 0.0, et = 0.0, single_electron_energy = 0.0, electronic_repulsion = 0.0;
     bool is_first = true;

@@ -7,7 +7,8 @@
 
 namespace dftcxx {
 
-MolecularGrid::MolecularGrid(const std::shared_ptr<Molecule>& mol_, int device_, bool verbose_) : mol(mol_), device(device_), verbose(verbose_) {}
+MolecularGrid::MolecularGrid(const std::shared_ptr<Molecule>& mol_, int device_, bool verbose_, int ngpus_)
+    : mol(mol_), device(device_), ngpus(ngpus_ < 1 ? 1 : ngpus_), verbose(verbose_) {}
 
 MolecularGrid::~MolecularGrid() {
     if (handle) dftgrid_destroy(handle);
@@ -61,7 +62,13 @@ void MolecularGrid::create_grid() {
         dftgrid_destroy(handle);
         handle = nullptr;
     }
-    check(dftgrid_create(&handle, &sys, &prm, device, 0, 1));
+    if (ngpus > 1) {
+        std::vector<int> devs(ngpus);
+        for (int i = 0; i < ngpus; i++) devs[i] = device + i;
+        check(dftgrid_create_multi(&handle, &sys, &prm, ngpus, devs.data()));  // one handle, ngpus devices, this process
+    } else {
+        check(dftgrid_create(&handle, &sys, &prm, device, 0, 1));
+    }
     check(dftgrid_build(handle));
     const auto elapsed = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now() - start);
     if (verbose) {
@@ -100,6 +107,27 @@ Mat MolecularGrid::calculate_exchange_correlation(double& exc) {
     check(dftgrid_xc(handle, XC.data(), &exc));
     return XC;
 }
+
+void MolecularGrid::fock(const Mat& P, bool include_xc, Mat& F, double& e_j, double& exc, double& nelec) {
+    if (!handle) throw std::runtime_error("create_grid has not been called");
+    check(dftgrid_fock(handle, P.data(), include_xc ? 1 : 0, F.data(), &e_j, &exc, &nelec));
+}
+
+void MolecularGrid::scf_init(const Mat& H, const Mat& X, unsigned int nocc, double alpha) {
+    if (!handle) throw std::runtime_error("create_grid has not been called");
+    check(dftgrid_scf_init(handle, H.data(), X.data(), (int)nocc, alpha));
+}
+
+void MolecularGrid::scf_step(bool include_xc, double out8[8]) { check(dftgrid_scf_step(handle, include_xc ? 1 : 0, out8)); }
+
+Mat MolecularGrid::scf_matrix(int which) const {
+    const unsigned int nb = mol->get_nr_bfs();
+    Mat M(nb, nb);
+    check(dftgrid_scf_get_matrix(handle, which, M.data()));
+    return M;
+}
+
+int MolecularGrid::gpus() const { return handle ? dftgrid_ngpus(handle) : ngpus; }
 
 std::vector<double> MolecularGrid::get_weights() const {
     std::vector<double> w(get_grid_size());

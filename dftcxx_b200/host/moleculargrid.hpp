@@ -13,7 +13,7 @@ namespace dftcxx {
 
 class MolecularGrid {
 public:
-    explicit MolecularGrid(const std::shared_ptr<Molecule>& mol, int device = 0, bool verbose = true);
+    explicit MolecularGrid(const std::shared_ptr<Molecule>& mol, int device = 0, bool verbose = true, int ngpus = 1);
     ~MolecularGrid();
     MolecularGrid(const MolecularGrid&) = delete;
     MolecularGrid& operator=(const MolecularGrid&) = delete;
@@ -27,6 +27,14 @@ public:
     Mat calculate_hartree_potential();                 // J
     Mat calculate_exchange_correlation(double& exc);   // XC matrix + E_xc (DFT::calculate_exchange_correlation_matrix)
 
+    // B200 engine extensions (no reference counterpart): the grid's whole Fock contribution in one contraction, and the
+    // device-resident SCF algebra (include/dftgrid.h: dftgrid_fock, dftgrid_scf_*)
+    void fock(const Mat& P, bool include_xc, Mat& F, double& e_j, double& exc, double& nelec);
+    void scf_init(const Mat& H, const Mat& X, unsigned int nocc, double alpha);
+    void scf_step(bool include_xc, double out8[8]);
+    Mat scf_matrix(int which) const;  // DFTGRID_SCF_P / DFTGRID_SCF_FGRID / ... (include/dftgrid.h)
+    int gpus() const;
+
     std::vector<double> get_weights() const;
     std::vector<double> get_densities() const;
     Mat get_amplitudes() const;  // basis functions x grid points, like the reference
@@ -37,7 +45,7 @@ private:
     std::shared_ptr<Molecule> mol;
     dftgrid_t* handle = nullptr;
     unsigned int radial_points = 15, lebedev_order = 7, lmax = 8;
-    int device;
+    int device, ngpus;
     bool verbose;
     bool density_pending = false;
 };

@@ -105,6 +105,10 @@ void Settings::set_default_settings() {
     if (has("radial_points") && parse_uint(get_value("radial_points"), v)) radial_points = v;
     if (has("lebedev_order") && parse_uint(get_value("lebedev_order"), v)) lebedev_order = v;
     if (has("lmax") && parse_uint(get_value("lmax"), v)) lmax = v;
+    if (has("gpus") && parse_uint(get_value("gpus"), v) && v >= 1) gpus = v;
+    const std::string scf = has("scf") ? get_value("scf") : "device";
+    const std::string fock = has("fock") ? get_value("fock") : "fused";
+    scf_mode = scf == "host" ? (fock == "separate" ? (unsigned)SCF_HOST_SEPARATE : (unsigned)SCF_HOST_FUSED) : (unsigned)SCF_DEVICE;
 }
 
 void Settings::set_grid_fineness(unsigned int fineness) {

@@ -23,6 +23,12 @@ public:
     unsigned int get_radial_points() const { return radial_points; }
     unsigned int get_lebedev_order() const { return lebedev_order; }
     unsigned int get_lmax() const { return lmax; }
+    // B200 engine keys (absent from stock inputs, which therefore run unchanged): `gpus = N` devices of this box driven
+    // from the one process (default 1), `scf = device|host` where the SCF algebra runs (default device), `fock =
+    // fused|separate` whether the host path asks the grid for F_grid = 2J + XC in one contraction or for J and XC
+    unsigned int get_gpus() const { return gpus; }
+    enum { SCF_DEVICE, SCF_HOST_FUSED, SCF_HOST_SEPARATE };
+    unsigned int get_scf_mode() const { return scf_mode; }
 
 private:
     Settings() {}
@@ -33,6 +39,7 @@ private:
     std::unordered_map<std::string, std::string> key_values;
     unsigned int radial_points = 15, lebedev_order = 7, lmax = 8;
     unsigned int hartree_evaluation = BECKE_GRID;
+    unsigned int gpus = 1, scf_mode = SCF_DEVICE;
 };
 
 // shared text helpers (boost::split(token_compress_on) / trim / strict lexical_cast semantics)

@@ -19,12 +19,17 @@
  *  - a handle is not re-entrant; calls come from one host thread (src/dft.cpp:95-104).
  *  - there is NO CPU fallback: without a CUDA device every compute call fails.
  *
- * Multi-GPU: one handle per process/GPU ("rank").  Grid points are sharded by
- * (atom, radial shell) units; dftgrid_comm_* wires an NCCL communicator between
- * the handles of one job (ids are exchanged by the host, e.g. torch.distributed).
+ * Multi-GPU, two ways.  (1) Single process (what `dftcxx -i ... --gpus N` uses, reference src/dft.cpp:57-61 has one
+ * MolecularGrid per run): dftgrid_create_multi returns ONE handle that drives N devices of the box with one worker
+ * thread per device; every call below accepts it and behaves as on a whole-grid handle.  (2) One process per GPU
+ * ("rank"): dftgrid_create(rank, nranks) + dftgrid_comm_* / dftgrid_peer_* wire NCCL and the peer-memory exchange
+ * between the handles of one job (ids are exchanged by the host, e.g. torch.distributed).  Grid points are sharded
+ * by (atom, radial shell) units either way.
  */
 #ifndef DFTGRID_H
 #define DFTGRID_H
+
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -62,6 +67,14 @@ int dftgrid_abi_version(void);
 /* MolecularGrid::MolecularGrid + set_grid_parameters (src/moleculargrid.cpp:32-35,175-179).
  * device: CUDA ordinal.  rank/nranks: this handle's shard of the grid (0/1 = whole grid). */
 int dftgrid_create(dftgrid_t** h, const dftgrid_system* sys, const dftgrid_params* prm, int device, int rank, int nranks);
+/* The same for ngpus devices of this box driven from one process (`int ngpus`): one handle, the
+ * grid sharded over devices[0..ngpus) (NULL = ordinals 0..ngpus-1), NCCL communicators from ncclCommInitAll for the small
+ * per-shell sums, the [J | XC] / F sum over peer memory (cudaDeviceEnablePeerAccess) when every device pair has a P2P
+ * route.  ngpus = 1 is dftgrid_create(device, 0, 1).  Results come back identical to the bit on every device; matrix
+ * downloads are split row-wise over the devices' PCIe links. */
+int dftgrid_create_multi(dftgrid_t** h, const dftgrid_system* sys, const dftgrid_params* prm, int ngpus, const int* devices);
+/* Number of devices behind a handle (1 unless it came from dftgrid_create_multi). */
+int dftgrid_ngpus(const dftgrid_t* h);
 /* RAII teardown of unique_ptr<MolecularGrid> (src/dft.h:44). */
 void dftgrid_destroy(dftgrid_t* h);
 
@@ -86,6 +99,9 @@ int dftgrid_peer_active(const dftgrid_t* h);
 /* The choice between the peer-memory path and NCCL must be the same on every rank: if dftgrid_peer_connect failed on
  * ANY rank (the host checks, e.g. with an all-reduce(min) of the return codes), every rank calls dftgrid_peer_disable. */
 int dftgrid_peer_disable(dftgrid_t* h);
+/* Bound of the peer kernels' spin-waits in seconds of wall time (default 60): a rank that does not show up within it
+ * makes the waiting ranks fail with an error instead of hanging their GPUs.  The error is fatal for the handle. */
+int dftgrid_peer_set_timeout(dftgrid_t* h, double seconds);
 
 /* MolecularGrid::create_grid (src/moleculargrid.cpp:193-261): points, quadrature weights, CGF amplitudes,
  * Becke weights; also factorises the radial Poisson operators used by dftgrid_hartree_J. */
@@ -112,6 +128,36 @@ int dftgrid_electron_count(dftgrid_t* h, double* nelec);
 /* One SCF iteration's whole grid path in one call (set_density, hartree_J, xc, electron_count with a single
  * upload of P and a single download of [J | XC | exc | nelec]); same results as the four calls above. */
 int dftgrid_iteration(dftgrid_t* h, const double* P, double* J, double* XC, double* exc, double* nelec);
+
+/* Fused Fock-matrix contribution of the grid (the only way src/dft.cpp:334 uses J and XC is F = H + 2J + XC):
+ * F_grid = 2J + XC = Phi^T diag(w (V_Hartree + v_xc)) Phi as ONE symmetric contraction (half the tensor work of
+ * dftgrid_iteration), E_J = 2 tr(P J) (src/dft.cpp:443) from the pointwise identity 1/2 sum_p w_p V_p rho_p[P], E_xc and
+ * the electron count.  include_xc = 0 leaves XC out (the reference's first iteration builds F from J(P0) alone,
+ * src/dft.cpp:219-226).  Same density / potential kernels as the calls above; F agrees with 2J + XC to rounding. */
+int dftgrid_fock(dftgrid_t* h, const double* P, int include_xc, double* F, double* e_j, double* exc, double* nelec);
+int dftgrid_fock_device(dftgrid_t* h, int include_xc);
+int dftgrid_download_fock(dftgrid_t* h, double* F, double* e_j, double* exc, double* nelec);
+
+/* Device-resident SCF algebra: DFT::calculate_density_matrix + DFT::calculate_energy
+ * (src/dft.cpp:330-366, 441-447) without leaving the GPU.  dftgrid_scf_init uploads the core Hamiltonian H and the
+ * orthogonalisation matrix X = U s^-1/2 (src/dft.cpp:300-316; both nb x nb ROW-major, X is not symmetric) once.  Every
+ * dftgrid_scf_step then forms F = H + F_grid of the previous step (F = H before the first one: core guess), F' = X^T F X,
+ * the projector D' onto the nocc lowest eigenvectors of F' (Palser-Manolopoulos purification: FP64 tensor-core products
+ * only, see csrc/kernels_scf.cuh), Pnew = X D' X^T, the reference's 50 % mixing P = (1 - alpha) Pnew + alpha P (first
+ * density unmixed), and runs the grid path for the new P as dftgrid_fock_device(include_xc).  P, F, H, X stay in HBM; the
+ * host receives out8 = { E_one = 2 tr(P H), E_J, E_xc, electron count, purification steps, idempotency residual,
+ * device ms of the algebra, device ms of the grid path }.  The reference's sequence is one step with include_xc = 0
+ * (DFT::construct_matrices, src/dft.cpp:219-226) followed by steps with include_xc = 1 (src/dft.cpp:100-103).  Fails
+ * (non-zero) when F' has no gap at the Fermi level; the caller then uses its own eigen-solver with dftgrid_fock. */
+int dftgrid_scf_init(dftgrid_t* h, const double* H, const double* X, int nocc, double alpha);
+int dftgrid_scf_step(dftgrid_t* h, int include_xc, double* out8);
+enum { DFTGRID_SCF_P = 0, DFTGRID_SCF_FGRID = 1, DFTGRID_SCF_FPRIME = 2, DFTGRID_SCF_DPRIME = 3 };
+int dftgrid_scf_get_matrix(dftgrid_t* h, int which, double* out /* nb x nb, row-major */);
+
+/* Page-lock / release a caller buffer (cudaHostRegister, portable across the devices of a multi-GPU handle) so that the
+ * matrix uploads and downloads above DMA straight from / into it; for hosts that do not link the CUDA runtime. */
+int dftgrid_host_register(void* p, size_t bytes);
+int dftgrid_host_unregister(void* p);
 
 /* Device-resident variant for benchmarking: P already uploaded by dftgrid_upload_density; runs all kernels and the
  * collectives, leaves results on the device; dftgrid_download_results copies them out. */
@@ -148,6 +194,9 @@ long dftgrid_launch_count(const dftgrid_t* h);
  * nsm+1 ints).  Chunk x belongs to the segment whose [begin, end) holds ((x * 2654435769) mod 2^32) >> 1. */
 int dftgrid_debug_contract_schedule(int nbp, long nchunk, int nsm, int max_segs, int* segs_out, int* cta_off_out, int* nctas, int* nsegs,
                                     int* block_chunks);
+/* The same for nz = 1 (fused Fock build) or 2 ([XC | J]) matrices. */
+int dftgrid_debug_contract_schedule_nz(int nbp, long nchunk, int nsm, int nz, int max_segs, int* segs_out, int* cta_off_out, int* nctas,
+                                       int* nsegs, int* block_chunks);
 
 enum {
     DFTGRID_T_POINTS = 0,   /* build: points + raw weights            */

@@ -58,7 +58,9 @@ def parity(name):
     mg.create_grid(box[0])
     J, XC, exc, nel = mg.iteration(g["P"])  # last collective through ncclAllReduce
     peer = False
-    if os.environ.get("DFTGRID_TEST_PEER", "1") == "1":
+    want_peer = os.environ.get("DFTGRID_TEST_PEER", "1") == "1"
+    can_p2p = all(torch.cuda.can_device_access_peer(a, b) for a in range(world) for b in range(world) if a != b)
+    if want_peer:
         peer = mg.connect_peers(dist)
         for _ in range(3):  # several epochs: the exchange buffers alternate and are re-used
             Jp, XCp, excp, nelp = mg.iteration(g["P"])
@@ -67,6 +69,13 @@ def parity(name):
         J, XC = Jp, XCp
     else:
         peer_close = True
+    # fused Fock build on the sharded grid (graph replay from the third call on): F = 2J + XC, E_J = 2 tr(P J)
+    for _ in range(3):
+        F, ej, excf, nelf = mg.fock(g["P"])
+    fock_ok = bool(np.max(np.abs(F - (2.0 * J + XC))) <= 2e-10 and abs(ej - 2.0 * np.trace(g["P"] @ J)) <= 1e-9 * max(1.0, abs(ej))
+                   and excf == exc and nelf == nel)
+    # a box whose GPUs can reach each other must really have taken the peer-memory path when it was asked for
+    peer_expected = want_peer and can_p2p
     # the sharded points are the matching slice of the single-rank grid
     idx = g["idx"]
     mine = (idx >= mg.point_offset) & (idx < mg.point_offset + mg.nloc)
@@ -80,9 +89,9 @@ def parity(name):
     if rank == 0:
         same = all(torch.equal(a, allr[0]) for a in allr)
         dJ, dXC = np.max(np.abs(J - g["J"])), np.max(np.abs(XC - g["XC"]))
-        good = same and peer_close and flags.item() == 1.0 and dJ <= 1e-10 and dXC <= 1e-10 and abs(exc - float(g["exc"])) <= 1e-10 and abs(nel - float(g["nel"])) <= 1e-9
-        print("PARITY_%s world=%d dJ=%.2e dXC=%.2e identical_on_all_ranks=%s shard_ok=%s peer_path=%s peer_vs_nccl_ok=%s" % (
-            "OK" if good else "FAIL", world, dJ, dXC, same, flags.item() == 1.0, peer, peer_close))
+        good = same and peer_close and fock_ok and peer == peer_expected and flags.item() == 1.0 and dJ <= 1e-10 and dXC <= 1e-10 and abs(exc - float(g["exc"])) <= 1e-10 and abs(nel - float(g["nel"])) <= 1e-9
+        print("PARITY_%s world=%d dJ=%.2e dXC=%.2e identical_on_all_ranks=%s shard_ok=%s peer_path=%s peer_expected=%s peer_vs_nccl_ok=%s fock_ok=%s" % (
+            "OK" if good else "FAIL", world, dJ, dXC, same, flags.item() == 1.0, peer, peer_expected, peer_close, fock_ok))
     mg.close()
     dist.destroy_process_group()
 

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
     lib.dftgrid_abi_version.restype = ctypes.c_int
-    assert lib.dftgrid_abi_version() == 1
+    assert lib.dftgrid_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():

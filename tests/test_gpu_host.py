@@ -23,27 +23,63 @@ def hostlib():
     L = ctypes.CDLL(os.path.join(ROOT, "dftcxx_b200", "libdfthost.so"))
     dp = ctypes.POINTER(ctypes.c_double)
     L.dfthost_scf.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp]
+    L.dfthost_scf2.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp]
     L.dfthost_last_error.restype = ctypes.c_char_p
     return L, dp
 
 
+MODES = {"device": 0, "host_fused": 1, "host_separate": 2}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("name", CASES)
-def test_scf_energies_match_reference_at_equal_iteration(name):
+def test_scf_energies_match_reference_at_equal_iteration(name, mode):
+    """The drop-in host in its three modes: SCF algebra on the device (default), host eigen-solver + fused Fock call on
+    page-locked matrices, host eigen-solver + the reference's four grid calls."""
     L, dp = hostlib()
     g = load_golden(name)
     ref = g["scf_energies"]
     nit = len(ref)
     e = np.zeros((nit, 6))
     enuc = ctypes.c_double()
-    n = L.dfthost_scf(os.path.join(M.DATA, "molecules", name + ".in").encode(), 0, nit, nit, e.ctypes.data_as(dp),
-                      ctypes.cast(ctypes.byref(enuc), dp))
+    nb = len(g["bf_nprim"])
+    P = np.zeros((nb, nb))
+    n = L.dfthost_scf2(os.path.join(M.DATA, "molecules", name + ".in").encode(), 0, 1, MODES[mode], nit, nit, e.ctypes.data_as(dp),
+                       ctypes.cast(ctypes.byref(enuc), dp), P.ctypes.data_as(dp))
     assert n == nit, L.dfthost_last_error()
+    assert np.array_equal(P, P.T) and abs(2.0 * np.trace(P @ g["scf_S"]) - float(g["nel"])) <= 1e-8  # tr(P S) = nocc
     assert abs(enuc.value - float(g["scf_enuc"])) < 1e-12
     assert np.max(np.abs(e[:, 0] - ref[:, 0])) <= TOL_ENERGY, np.abs(e[:, 0] - ref[:, 0])
     assert np.max(np.abs(e[:, 1] - ref[:, 1])) <= TOL_ENERGY  # E_xc
     assert np.max(np.abs(e[:, 2] - ref[:, 2])) <= TOL_ENERGY  # E_one
     assert np.max(np.abs(e[:, 3] - ref[:, 3])) <= TOL_ENERGY  # E_J
     assert np.max(np.abs(e[:, 4] - ref[:, 4])) <= 1e-9        # electron count
+
+
+@pytest.mark.parametrize("name", ["h2o_p631", "benzene_p631_fine", "h2o8_p631_fine"])
+def test_scf_on_two_gpus_from_one_process(name):
+    """`dftcxx -i ... --gpus 2`: the C++ host drives two devices through ONE dftgrid_create_multi handle."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    L, dp = hostlib()
+    g = load_golden(name)
+    ref = g["scf_energies"]
+    nit = len(ref)
+    for mode in (0, 1):
+        e = np.zeros((nit, 6))
+        n = L.dfthost_scf2(os.path.join(M.DATA, "molecules", name + ".in").encode(), 0, 2, mode, nit, nit, e.ctypes.data_as(dp), None, None)
+        assert n == nit, L.dfthost_last_error()
+        assert np.max(np.abs(e[:, 0] - ref[:, 0])) <= TOL_ENERGY, np.abs(e[:, 0] - ref[:, 0])
+        assert np.max(np.abs(e[:, 4] - ref[:, 4])) <= 1e-9
+    exe = os.path.join(ROOT, "dftcxx_b200", "bin", "dftcxx")
+    r = subprocess.run([exe, "-i", os.path.join(M.DATA, "molecules", name + ".in"), "--gpus", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    rows = re.findall(r"^\s*(\d+)\s+(-?\d+\.\d{7})\s+(\d+\.\d\d) \(\s*(\d+)\)", r.stdout, flags=re.M)
+    assert len(rows) >= nit
+    for (it, et, nel, nelec), rr in zip(rows, ref):
+        assert abs(float(et) - rr[0]) < 1.5e-7
 
 
 def test_scf_stopping_rule_and_iteration_count():
