@@ -12,8 +12,13 @@
 // shared memory with bulk asynchronous copies that signal an mbarrier; the eight DMMA warps never touch global memory
 // in their main loop, wait on the "full" barrier of a stage and release it through an "empty" barrier.
 //
-// Shared-memory tiles are padded so that every fragment load is bank-conflict free:
-//   [rows][32+4] doubles for "row = lane/4, col = lane%4" accesses, [rows][128+8] for "row = lane%4, col = lane/4".
+// Shared-memory tiles are padded so that every fragment load is bank-conflict free: a 64-bit load of a warp is served as
+// two half-warp wavefronts of 16 x 8 bytes, so the 16 addresses of a half warp (lane = 4 g + q, g = 0..3, q = 0..3) must
+// fall into 16 distinct 8-byte banks, i.e. be distinct mod 16 doubles:
+//   [rows][32+4]  for "row = lane/4, col = lane%4" accesses: 36 g + q  = 4 g + q (mod 16)  -> 0..15
+//   [rows][128+4] for "row = lane%4, col = lane/4" accesses: 132 q + g = 4 q + g (mod 16)  -> 0..15
+// (Round 1 used 128+8 for the second kind: 136 q + g = 8 q + g (mod 16) collides for q = 0 / 2 and 1 / 3 — the 2-way
+// conflicts ncu counted as l1tex__data_bank_conflicts_pipe_lsu_mem_shared; rows stay 16-byte aligned for the bulk copies.)
 #pragma once
 #include "common.cuh"
 
@@ -60,9 +65,9 @@ constexpr int kTileN = 128;
 constexpr int kTileK = 32;
 constexpr int kLdK = kTileK + 4;    // 36
 #ifndef DFG_LDN_PAD
-#define DFG_LDN_PAD 8
+#define DFG_LDN_PAD 4  // developer A/B: 8 was round 1's value
 #endif
-constexpr int kLdN = kTileN + DFG_LDN_PAD;    // 136 (pad 8) or 132 (pad 4)
+constexpr int kLdN = kTileN + DFG_LDN_PAD;    // 132
 constexpr int kStages = 3;
 
 // flags[c] = 1 when any amplitude of the 32 rows of chunk c is non-zero.  Far from every nucleus exp(-alpha r^2)

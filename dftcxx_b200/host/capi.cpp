@@ -7,6 +7,7 @@
 
 namespace {
 thread_local std::string g_err;
+std::vector<dftcxx::ScfRecord> g_last;  // the SCF table of the most recent dfthost_scf* run
 }
 
 extern "C" {
@@ -28,6 +29,7 @@ int dfthost_scf2(const char* infile, int device, int ngpus, int scf_mode, int fi
         else
             dft.scf((unsigned)max_iter);
         const auto& h = dft.history();
+        g_last = h;
         int n = 0;
         for (const auto& r : h) {
             if (n >= max_iter) break;
@@ -53,6 +55,20 @@ int dfthost_scf2(const char* infile, int device, int ngpus, int scf_mode, int fi
 
 int dfthost_scf(const char* infile, int device, int fixed_iterations, int max_iter, double* energies, double* enuc) {
     return dfthost_scf2(infile, device, -1, -1, fixed_iterations, max_iter, energies, enuc, nullptr);
+}
+
+// per iteration of the most recent run: wall ms, device ms of the SCF algebra, device ms of the grid path, purification steps
+int dfthost_last_timings(double* out, int max_iter) {
+    int n = 0;
+    for (const auto& r : g_last) {
+        if (n >= max_iter) break;
+        double* t = out + 4 * n++;
+        t[0] = r.ms;
+        t[1] = r.ms_algebra;
+        t[2] = r.ms_grid;
+        t[3] = r.purification_steps;
+    }
+    return n;
 }
 
 // host-only: S, T, V (nb x nb each) for an input file; no GPU needed.  Returns nb or < 0.

@@ -10,7 +10,7 @@
 namespace dftcxx {
 
 using clk = std::chrono::system_clock;
-static long ms_since(const clk::time_point& t0) { return (long)std::chrono::duration_cast<std::chrono::milliseconds>(clk::now() - t0).count(); }
+static double ms_since(const clk::time_point& t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
 
 DFT::DFT(const std::string& filename, int device_, bool verbose_, int ngpus_, int scf_mode_)
     : ngpus_opt(ngpus_), scf_mode_opt(scf_mode_), verbose(verbose_), device(device_) {
@@ -41,7 +41,7 @@ void DFT::add_molecule() {
     const auto t0 = clk::now();
     construct_matrices();
     if (verbose) {
-        std::printf("Total time: %ld ms\n", ms_since(t0));
+        std::printf("Total time: %ld ms\n", (long)ms_since(t0));
         std::cout << std::endl;
     }
 }
@@ -214,7 +214,7 @@ double DFT::scf_step() {
     rec.e_one = single_electron_energy;
     rec.e_j = electronic_repulsion;
     rec.nelec_grid = nelec_grid;
-    rec.ms = (double)ms_since(t0);
+    rec.ms = ms_since(t0);
     records.push_back(rec);
     return et;
 }

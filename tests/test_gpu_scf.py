@@ -49,8 +49,10 @@ def test_device_scf_matches_reference_trace(name):
         for k in (1, 2, 3):  # E_xc, E_one, E_J
             assert np.max(np.abs(e[:, k] - ref[:, k])) <= TOL_ENERGY
         assert np.max(np.abs(e[:, 4] - ref[:, 4])) <= 1e-9
-        # the density matrix of the probe iteration: 1e-10 elementwise (the projector is conditioned like eps*width/gap)
-        assert np.max(np.abs(pr["P"] - g["scf_P"])) <= 1e-10
+        # the density matrix of the probe iteration, elementwise: P = X D' X^T, so an error of D' (conditioned like
+        # eps*width/gap in the reference's eigenvectors as much as here) is amplified by |X|_2^2 = 1/lambda_min(S)
+        # (538 for the toy ethane geometry, 1435 for benzene): 1e-10, or 1e-12 |X|_2^2 where that is larger
+        assert np.max(np.abs(pr["P"] - g["scf_P"])) <= max(1e-10, 1e-12 * np.linalg.norm(g["scf_X"], 2) ** 2)
         assert np.array_equal(pr["P"], pr["P"].T)
         # the purified projector against the eigenvectors of the device's own F'
         n = pr["Fp"].shape[0]
