@@ -315,6 +315,8 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSc
     static const char* dc = std::getenv("DFTGRID_DIAG_COST");
     static const char* ec = std::getenv("DFTGRID_EDGE_DIAG_COST");
     static const char* l2e = std::getenv("DFTGRID_L2_BLOCK_MB");
+    static const char* n32c = std::getenv("DFTGRID_N32_COST");
+    static const char* d32c = std::getenv("DFTGRID_D32_COST");
     double W1 = 0.0;  // cost of all items for one chunk
     for (int it = 0; it < nitems; it++) {
         const int ti = S.pairs[2 * (it % npairs)], tj = S.pairs[2 * (it % npairs) + 1];
@@ -322,9 +324,13 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSc
         // (H2O)64, (H2O)32 and C40H82: a 64-wide edge tile issues half the DMMAs but pays the same loads (10.5), a
         // diagonal tile issues 17 of 32 DMMAs per warp (11.5), the 64-wide diagonal tile 8 of 32 (6.5; under-estimating
         // it makes its CTA the straggler, 5 costs 14 %)
-        const bool narrow = std::min(kTileN, nbp - tj * kTileN) <= 64;
+        // a 32-wide edge tile (nb = 524 -> nbp = 544) issues a quarter of the DMMAs for the same A loads (6.5); its
+        // diagonal tile keeps four warps busy with 4 DMMAs per k4-step (3)
+        const int wj = std::min(kTileN, nbp - tj * kTileN);
+        const bool narrow = wj <= 64, narrow32 = wj <= 32;
         const double c_narrow = nc ? std::atof(nc) : 10.5, c_diag = dc ? std::atof(dc) : 11.5, c_edge_diag = ec ? std::atof(ec) : 6.5;
-        cost[it] = ti == tj ? (narrow ? c_edge_diag : c_diag) : (narrow ? c_narrow : 20.0);
+        const double c_n32 = n32c ? std::atof(n32c) : 6.5, c_d32 = d32c ? std::atof(d32c) : 3.0;
+        cost[it] = ti == tj ? (narrow32 ? c_d32 : narrow ? c_edge_diag : c_diag) : (narrow32 ? c_n32 : narrow ? c_narrow : 20.0);
         W1 += cost[it];
     }
     // block length (the period at which a CTA with several segments alternates between them): ~120 MB of Phi rows.
@@ -640,7 +646,7 @@ void do_build(dftgrid* h) {
     record(h, 1);
     if (g.nloc > 0) {
         k_becke<<<(unsigned)((g.nloc + kBeckeWarps - 1) / kBeckeWarps), kBeckeWarps * 32, becke_smem, st>>>(
-            g, h->d_atom_xyz.p, nullptr, h->d_Rdist.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p, h->d_wb.p);
+            g, h->d_atom_xyz.p, h->d_Rdist.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_w.p, h->d_wb.p);
         h->launches++;
     }
     record(h, 2);

@@ -461,6 +461,62 @@ struct ConModeNarrow {
             }
     }
 };
+// 32-wide edge tile (nbp = 128 k + 32, e.g. nb = 524): 4 column tiles instead of 8
+struct ConModeNarrow32 {
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 4>(st, acc, warp, lane); }
+    template <bool LOAD>
+    static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
+        const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                double2* p = reinterpret_cast<double2*>(out + (warp * 16 + mt * 8 + g) * kTileN + nt * 8 + q * 2);
+                if (LOAD) {
+                    const double2 v = *p;
+                    acc[mt * 4 + nt][0] = v.x;
+                    acc[mt * 4 + nt][1] = v.y;
+                } else {
+                    *p = make_double2(acc[mt * 4 + nt][0], acc[mt * 4 + nt][1]);
+                }
+            }
+    }
+};
+// 32-wide diagonal edge tile: warps 0-3 own row tile w against the 4 column tiles, warps 4-7 only follow the pipeline
+struct ConModeDiagEdge32 {
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) {
+        if (warp >= 4) return;
+        const double* As = st;
+        const double* ds = st + 2 * kTileK * kLdN;
+        const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+        for (int kk = 0; kk < kTileK; kk += 4) {
+            double b[4];
+            const double dv = ds[kk + q];
+            const double a0 = As[(kk + q) * kLdN + warp * 8 + g] * dv;
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) b[nt] = As[(kk + q) * kLdN + nt * 8 + g];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) dmma884(acc[nt][0], acc[nt][1], a0, b[nt]);
+        }
+    }
+    template <bool LOAD>
+    static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
+        if (warp >= 4) return;
+        const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            double2* p = reinterpret_cast<double2*>(out + (warp * 8 + g) * kTileN + nt * 8 + q * 2);
+            if (LOAD) {
+                const double2 v = *p;
+                acc[nt][0] = v.x;
+                acc[nt][1] = v.y;
+            } else {
+                *p = make_double2(acc[nt][0], acc[nt][1]);
+            }
+        }
+    }
+};
 struct ConModeDiagEdge {
     static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage_diag_edge(st, acc, warp, lane); }
     template <bool LOAD>
@@ -536,13 +592,18 @@ __device__ __forceinline__ void con_segment_blocks(const double* sm, unsigned lo
                                                    int b_begin, int b_end, bool fresh) {
     const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
     const bool diag = ti == tj;
-    const bool narrow = min(kTileN, nbp - tj * kTileN) <= 64;
+    const int wj = min(kTileN, nbp - tj * kTileN);
+    const bool narrow = wj <= 64, narrow32 = wj <= 32;
 #define DFG_SEG_ARGS sm, full, empty, n, warp, lane, sg, out, nchunk, bc, b_begin, b_end, fresh
     if (!diag) {
-        if (narrow)
+        if (narrow32)
+            con_segment_blocks_mode<ConModeNarrow32>(DFG_SEG_ARGS);
+        else if (narrow)
             con_segment_blocks_mode<ConModeNarrow>(DFG_SEG_ARGS);
         else
             con_segment_blocks_mode<ConModeFull>(DFG_SEG_ARGS);
+    } else if (narrow32) {
+        con_segment_blocks_mode<ConModeDiagEdge32>(DFG_SEG_ARGS);
     } else if (narrow) {
         con_segment_blocks_mode<ConModeDiagEdge>(DFG_SEG_ARGS);
     } else {

@@ -56,7 +56,7 @@ __device__ __forceinline__ double becke_cutoff(double mu) {
 constexpr int kBeckeWarps = 4;
 
 __global__ void __launch_bounds__(kBeckeWarps * 32)
-k_becke(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ Rinv_unused,
+k_becke(GridShape g, const double* __restrict__ atom_xyz,
         const double* __restrict__ Rdist /*[natoms][natoms] |R_j-R_k|*/, const double* __restrict__ px,
         const double* __restrict__ py, const double* __restrict__ pz, double* __restrict__ w, double* __restrict__ wb) {
     extern __shared__ double sm[];

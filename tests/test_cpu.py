@@ -271,9 +271,10 @@ def test_c_restatement_matches_reference_golden(name):
     o.close()
 
 
+@pytest.mark.parametrize("nz", [2, 1], ids=["xc_and_j", "fused_fock"])
 @pytest.mark.parametrize("nbp,nchunk,nsm", [(32, 155, 148), (96, 1095, 148), (832, 16800, 148), (832, 2100, 148), (544, 312000, 148),
-                                           (2048, 5000, 148), (832, 0, 148), (128, 3, 148), (832, 16800, 7)])
-def test_contraction_schedule_tiles_every_item_exactly_once(nbp, nchunk, nsm):
+                                           (2048, 5000, 148), (832, 0, 148), (128, 3, 148), (832, 16800, 7), (448, 9000, 148)])
+def test_contraction_schedule_tiles_every_item_exactly_once(nbp, nchunk, nsm, nz):
     """Host logic of the [J | XC] stream-K schedule (pure arithmetic, no device): for every (matrix, tile pair) item the
     segments' fixed-point fraction ranges tile [0, 2^31) without gap or overlap, so the device-side golden-ratio hash
     assigns every chunk to exactly one segment of every item; the CTAs' cost shares are equal; a CTA has few segments."""
@@ -283,13 +284,13 @@ def test_contraction_schedule_tiles_every_item_exactly_once(nbp, nchunk, nsm):
 
     L = G.lib()
     ip = C.POINTER(C.c_int)
-    L.dftgrid_debug_contract_schedule.argtypes = [C.c_int, C.c_long, C.c_int, C.c_int, ip, ip, ip, ip, ip]
+    L.dftgrid_debug_contract_schedule_nz.argtypes = [C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip]
     max_segs = 4096
     segs = np.zeros((max_segs, 4), dtype=np.int32)
     cta_off = np.zeros(nsm + 1, dtype=np.int32)
     nctas, nsegs, bc = C.c_int(), C.c_int(), C.c_int()
-    rc = L.dftgrid_debug_contract_schedule(nbp, nchunk, nsm, max_segs, segs.ctypes.data_as(ip), cta_off.ctypes.data_as(ip), C.byref(nctas),
-                                           C.byref(nsegs), C.byref(bc))
+    rc = L.dftgrid_debug_contract_schedule_nz(nbp, nchunk, nsm, nz, max_segs, segs.ctypes.data_as(ip), cta_off.ctypes.data_as(ip), C.byref(nctas),
+                                              C.byref(nsegs), C.byref(bc))
     assert rc == 0, L.dftgrid_last_error()
     segs = segs[:nsegs.value]
     z, pair = segs[:, 0], segs[:, 1]
@@ -300,7 +301,7 @@ def test_contraction_schedule_tiles_every_item_exactly_once(nbp, nchunk, nsm):
     assert cta_off[0] == 0 and cta_off[nctas.value] == nsegs.value and np.all(np.diff(cta_off[:nctas.value + 1]) >= 0)
     item = z.astype(np.int64) * npairs + pair
     assert np.all(np.diff(item) >= 0), "segments must be item-major (the reduction indexes them by item)"
-    for it in range(2 * npairs):
+    for it in range(nz * npairs):
         m = item == it
         assert m.any(), "every item needs at least one segment (its partial tile is read by the reduction)"
         b, e = tb[m], te[m]
@@ -308,7 +309,7 @@ def test_contraction_schedule_tiles_every_item_exactly_once(nbp, nchunk, nsm):
     # every chunk is owned exactly once per item under the device's hash
     x = np.arange(min(nchunk, 20000), dtype=np.uint64)
     u = ((x * np.uint64(2654435769)) & np.uint64(0xFFFFFFFF)) >> np.uint64(1)
-    for it in (0, npairs, 2 * npairs - 1):
+    for it in (0, npairs - 1, nz * npairs - 1):
         m = item == it
         owners = ((u[:, None] >= tb[m][None, :].astype(np.uint64)) & (u[:, None] < te[m][None, :].astype(np.uint64))).sum(axis=1)
         assert np.all(owners == 1)
@@ -322,11 +323,13 @@ def test_contraction_schedule_tiles_every_item_exactly_once(nbp, nchunk, nsm):
                     i, j = a, a + k
                     break
                 k -= nt - a
-            narrow = min(128, nbp - j * 128) <= 64
-            return (6.5 if narrow else 11.5) if i == j else (10.5 if narrow else 20.0)
+            wj = min(128, nbp - j * 128)
+            if wj <= 32:
+                return 3.0 if i == j else 6.5
+            return (6.5 if wj <= 64 else 11.5) if i == j else (10.5 if wj <= 64 else 20.0)
         share = [sum(cost(int(pair[s])) * (te[s] - tb[s]) / float(1 << 31) for s in range(cta_off[c], cta_off[c + 1])) for c in range(nctas.value)]
         assert max(share) - min(share) <= 1e-6 * max(share)
-        assert max(np.diff(cta_off[:nctas.value + 1])) <= 4 or nctas.value < 2 * npairs
+        assert max(np.diff(cta_off[:nctas.value + 1])) <= 4 or nctas.value < nz * npairs
 
 
 def test_host_eigensolver_is_thread_count_independent():

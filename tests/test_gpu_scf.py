@@ -90,4 +90,7 @@ def test_device_scf_is_deterministic_and_multi_gpu_identical():
             _, e3, p3 = run_trace(mg, g, 3)
         finally:
             mg.close()
-        assert np.max(np.abs(e3[:, :5] - e1[:, :5])) <= 1e-9 and np.max(np.abs(p3["P"] - p1["P"])) <= 1e-11
+        # two devices sum the shards' F in a different order than one device: rounding-level differences, amplified in P by
+        # |X|_2^2 (1435 for benzene) like in the fixture comparison above
+        assert np.max(np.abs(e3[:, :5] - e1[:, :5])) <= 1e-9
+        assert np.max(np.abs(p3["P"] - p1["P"])) <= max(1e-11, 1e-13 * np.linalg.norm(g["scf_X"], 2) ** 2)
