@@ -2047,6 +2047,15 @@ int dftgrid_scf_get_matrix(dftgrid_t* h, int which, double* out) {
     });
 }
 
+int dftgrid_debug_set_stress(dftgrid_t* h, int mode) {
+    GROUP_FORWARD(h, dftgrid_debug_set_stress(s, mode));
+    return guarded([&] {
+        use_device(h);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpyToSymbol(c_stress_mode, &mode, sizeof mode));
+    });
+}
+
 int dftgrid_host_register(void* p, size_t bytes) {
     return guarded([&] { CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable)); });
 }

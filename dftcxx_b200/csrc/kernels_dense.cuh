@@ -59,6 +59,21 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
                  : "memory");
 }
 
+// Test hook (dftgrid_debug_set_stress): pseudo-random delays in the producer (bit 0) and / or consumer (bit 1) warps of the
+// two mbarrier pipelines.  Any ordering bug between the bulk copies and the fragment loads (a stage overwritten before its
+// last reader, a stage read before its bytes landed) shows up as changed bits under the perturbed timing; the results must
+// stay identical to the unperturbed run (tests/test_gpu_stress.py).  Zero in production: one uniform constant load per stage.
+__constant__ int c_stress_mode = 0;
+__device__ __forceinline__ void stress_delay(int bit, unsigned n) {
+    if (c_stress_mode & bit) {
+        unsigned h = (n * 2654435761u) ^ (blockIdx.x * 40503u) ^ ((threadIdx.x >> 5) * 9176u);
+        h ^= h >> 13;
+        h *= 0x5bd1e995u;
+        h ^= h >> 15;
+        if ((h & 3u) == 0u) __nanosleep(h % 3000u);
+    }
+}
+
 constexpr int kDenseThreads = 256;  // 8 DMMA warps
 constexpr int kTileM = 128;
 constexpr int kTileN = 128;
@@ -201,6 +216,7 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
             double* st = sm + (size_t)stage * kRhoStageDoubles;
             const int slab = ld.slab * kTileN, kc = ld.chunk() * kTileK;
             const unsigned wb = (unsigned)min(kTileN, nbp - slab) * 8u;
+            stress_delay(1, (unsigned)it);
             mbar_wait(empty + stage, (round & 1u) ^ 1u);
             if (lane == 0) mbar_arrive_expect_tx(full + stage, 32u * kTileK * 8u + 8u * wb);
             __syncwarp();
@@ -236,6 +252,7 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
         const int rel = cs.rel();
         const bool h0 = blk0 < nblk && (rel < 0 || blk0 <= rel), h1 = blk1 < nblk && (rel < 0 || blk1 <= rel);
         mbar_wait(full + stage, round & 1u);
+        stress_delay(2, (unsigned)it);
         const double* st = sm + (size_t)stage * kRhoStageDoubles;
         if (h0 && h1)
             rho_mma_stage<true, true>(st, acc, wm, blk0 * 32, blk1 * 32, lane);
@@ -413,6 +430,7 @@ __device__ __forceinline__ void con_run_segment(const double* sm, unsigned long 
     for (int c = 0; c < nchunks; c++, n++) {
         const unsigned stage = n % kStages, round = n / kStages;
         mbar_wait(full + stage, round & 1u);
+        stress_delay(2, n);
         op(sm + (size_t)stage * kConStageDoubles);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);
@@ -665,6 +683,7 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
                         const size_t row0 = (size_t)__shfl_sync(0xffffffffu, my_chunk, src) * kTileK;
                         const unsigned stage = n % kStages, round = n / kStages;
                         double* st = sm + (size_t)stage * kConStageDoubles;
+                        stress_delay(1, n);
                         mbar_wait(empty + stage, (round & 1u) ^ 1u);
                         if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes);
                         __syncwarp();

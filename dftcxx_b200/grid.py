@@ -50,6 +50,7 @@ def lib():
     L.dftgrid_scf_init.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double]
     L.dftgrid_scf_step.argtypes = [C.c_void_p, C.c_int, _dp]
     L.dftgrid_scf_get_matrix.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.dftgrid_debug_set_stress.argtypes = [C.c_void_p, C.c_int]
     L.dftgrid_destroy.argtypes = [C.c_void_p]
     L.dftgrid_destroy.restype = None
     L.dftgrid_comm_unique_id.argtypes = [C.c_void_p]
@@ -278,6 +279,10 @@ class MolecularGrid:
         out = np.zeros((self.nbf, self.nbf))
         self._ck(lib().dftgrid_scf_get_matrix(self.h, {"P": 0, "F_grid": 1, "F_prime": 2, "D_prime": 3}[which], _ptr(out)))
         return out
+
+    def debug_set_stress(self, mode):
+        """Test hook: random delays in the producer (1) / consumer (2) warps of the tensor kernels' pipelines."""
+        self._ck(lib().dftgrid_debug_set_stress(self.h, int(mode)))
 
     def peer_active(self):
         return lib().dftgrid_peer_active(self.h) == 1

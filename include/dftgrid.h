@@ -198,6 +198,10 @@ int dftgrid_debug_contract_schedule(int nbp, long nchunk, int nsm, int max_segs,
 int dftgrid_debug_contract_schedule_nz(int nbp, long nchunk, int nsm, int nz, int max_segs, int* segs_out, int* cta_off_out, int* nctas,
                                        int* nsegs, int* block_chunks);
 
+/* Test hook: perturb the timing of the producer (bit 0) / consumer (bit 1) warps of the two tensor kernels' mbarrier
+ * pipelines with pseudo-random delays on this handle's device(s); results must not change by a bit.  0 = off (default). */
+int dftgrid_debug_set_stress(dftgrid_t* h, int mode);
+
 enum {
     DFTGRID_T_POINTS = 0,   /* build: points + raw weights            */
     DFTGRID_T_BECKE = 1,    /* build: Becke fuzzy-cell weights        */
