@@ -109,6 +109,9 @@ struct dftgrid {
     // device: per iteration
     DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_qatom2, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
     DevBuf<int> d_pairs, d_chunk_ids;
+    DevBuf<unsigned long long> d_chunk_mask;  // screening map of the active chunks (k_chunk_masks), aligned with d_chunk_ids
+    bool screened = false;
+    double screen_work_fraction = 1.0;
     // stream-K schedules of the contraction: [0] two matrices (XC, J), [1] one matrix (fused Fock build)
     struct DevSchedule {
         DevBuf<ConSeg> segs;
@@ -300,7 +303,10 @@ struct ContractSchedule {
 };
 
 // Pure host arithmetic (no device): also exported as dftgrid_debug_contract_schedule for the CPU test-suite.
-void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSchedule& S) {
+// item_frac (optional, [npairs]): mean fraction of a full stage's DMMA work that a chunk costs the tile pair under the
+// screening map (1 = every block of every chunk significant); the items' costs are scaled by it so that the CTAs' shares
+// stay equal in time.
+void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSchedule& S, const std::vector<double>* item_frac = nullptr) {
     S = ContractSchedule();
     const int nt = (nbp + kTileM - 1) / kTileM;
     for (int i = 0; i < nt; i++)
@@ -331,6 +337,7 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSc
         const double c_narrow = nc ? std::atof(nc) : 10.5, c_diag = dc ? std::atof(dc) : 11.5, c_edge_diag = ec ? std::atof(ec) : 6.5;
         const double c_n32 = n32c ? std::atof(n32c) : 6.5, c_d32 = d32c ? std::atof(d32c) : 3.0;
         cost[it] = ti == tj ? (narrow32 ? c_d32 : narrow ? c_edge_diag : c_diag) : (narrow32 ? c_n32 : narrow ? c_narrow : 20.0);
+        if (item_frac) cost[it] *= std::max(0.02, (*item_frac)[it % npairs]);  // never zero: every item keeps a segment
         W1 += cost[it];
     }
     // block length (the period at which a CTA with several segments alternates between them): ~120 MB of Phi rows.
@@ -393,12 +400,12 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSc
     }
 }
 
-void build_contract_schedule(dftgrid* h, long nchunk, int nsm) {
+void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector<double>* item_frac) {
     cudaStream_t st = h->stream;
     size_t max_segs = 0;
     for (int k = 0; k < 2; k++) {
         ContractSchedule S;
-        compute_contract_schedule(h->nbp, nchunk, nsm, k == 0 ? 2 : 1, S);
+        compute_contract_schedule(h->nbp, nchunk, nsm, k == 0 ? 2 : 1, S, item_frac);
         h->npairs = S.npairs;
         h->con_bc = S.bc;
         if (k == 0) h->d_pairs.upload(S.pairs, st);
@@ -421,22 +428,57 @@ void build_active_lists(dftgrid* h, int nsm) {
     const GridShape& g = h->g;
     cudaStream_t st = h->stream;
     const long nchunk = (g.nloc + kTileK - 1) / kTileK;
-    std::vector<int> flags((size_t)nchunk, 1);
-    if (nchunk > 0 && !std::getenv("DFTGRID_NO_ZERO_SKIP")) {  // developer A/B switch
-        DevBuf<int> d_flags;
-        d_flags.alloc((size_t)nchunk);
-        k_chunk_flags<<<(unsigned)((nchunk * 32 + 255) / 256), 256, 0, st>>>(h->d_phi.p, nchunk, h->nbp, d_flags.p);
+    const int nblk = h->nbp / 32;
+    // Screening map (k_chunk_masks).  DFTGRID_SCREEN_TAU: threshold on |phi| (default 1e-20; 0 = exact zeros only; negative
+    // or DFTGRID_NO_ZERO_SKIP = no skipping at all, developer A/B switches).  More than 64 column blocks: no map.
+    double tau = 1e-20;
+    if (const char* e = std::getenv("DFTGRID_SCREEN_TAU")) tau = std::atof(e);
+    const bool screen = nchunk > 0 && tau >= 0.0 && nblk <= 64 && !std::getenv("DFTGRID_NO_ZERO_SKIP");
+    std::vector<unsigned long long> masks((size_t)nchunk, ~0ull);
+    if (screen) {
+        DevBuf<unsigned long long> d_masks;
+        d_masks.alloc((size_t)nchunk);
+        k_chunk_masks<<<(unsigned)((nchunk * 32 + 255) / 256), 256, 0, st>>>(h->d_phi.p, nchunk, h->nbp, tau, d_masks.p);
         h->launches++;
-        CK(cudaMemcpyAsync(flags.data(), d_flags.p, (size_t)nchunk * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(masks.data(), d_masks.p, (size_t)nchunk * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
+    std::vector<int> flags((size_t)nchunk, 1);
+    for (long c = 0; c < nchunk; c++) flags[c] = masks[c] != 0ull;
     std::vector<int> chunk_ids;
     for (long c = 0; c < nchunk; c++)
         if (flags[c]) chunk_ids.push_back((int)c);
     h->n_active_chunks = (long)chunk_ids.size();
-    while (chunk_ids.size() % 4 != 0 || chunk_ids.empty()) chunk_ids.push_back(-1);  // k_rho_tma reads groups of four
+    std::vector<unsigned long long> act_masks;
+    for (int c : chunk_ids) act_masks.push_back(masks[c]);
+    while (chunk_ids.size() % 4 != 0 || chunk_ids.empty()) {  // k_rho_tma reads groups of four
+        chunk_ids.push_back(-1);
+        act_masks.push_back(0ull);
+    }
     h->d_chunk_ids.upload(chunk_ids, st);
+    h->screened = screen;
+    if (screen) h->d_chunk_mask.upload(act_masks, st);
     CK(cudaStreamSynchronize(st));
+    // work fraction of every tile pair under the map: a stage costs the pair as much as its busiest warp, i.e. (any
+    // significant block of tile i) x (fraction of tile j's blocks that are significant); skipped chunks cost nothing
+    std::vector<double> item_frac;
+    if (screen && h->n_active_chunks > 0) {
+        const int nt = (h->nbp + kTileM - 1) / kTileM;
+        for (int ti = 0; ti < nt; ti++)
+            for (int tj = ti; tj < nt; tj++) {
+                const int nbj = std::min(4, nblk - 4 * tj);
+                const unsigned long long mi = 0xFull << (4 * ti), mj = (nbj >= 4 ? 0xFull : ((1ull << nbj) - 1ull)) << (4 * tj);
+                double acc = 0.0;
+                for (long x = 0; x < h->n_active_chunks; x++) {
+                    const unsigned long long cm = act_masks[x];
+                    if ((cm & mi) && (cm & mj)) acc += (double)__builtin_popcountll(cm & mj) / nbj;
+                }
+                item_frac.push_back(acc / (double)h->n_active_chunks);
+            }
+        double mean = 0.0;
+        for (double f : item_frac) mean += f;
+        h->screen_work_fraction = item_frac.empty() ? 1.0 : mean / item_frac.size();
+    }
     {
         // k_rho_tma work items: one CTA per 128-point tile when that gives many waves over the SMs; with few waves
         // (sharded grids, small molecules) the tail wave costs up to 1/waves, so a tile's column slabs are dealt to 2 or 3 CTAs
@@ -451,7 +493,7 @@ void build_active_lists(dftgrid* h, int nsm) {
             h->d_rho_part.zero(st);  // skipped (all-zero) chunks are never written
         }
     }
-    build_contract_schedule(h, h->n_active_chunks, nsm);
+    build_contract_schedule(h, h->n_active_chunks, nsm, item_frac.empty() ? nullptr : &item_frac);
 }
 
 // Sort the (local point, source atom) pairs of the cross-atom interpolation into (atom, spline interval) bins.
@@ -750,10 +792,11 @@ void run_density(dftgrid* h) {
     if (g.nloc > 0) {
         if (h->n_active_chunks > 0) {
             const unsigned tiles = (unsigned)((h->n_active_chunks + 3) / 4);
+            const unsigned long long* cmask = h->screened ? h->d_chunk_mask.p : nullptr;
             if (h->rho_split == 1) {
-                k_rho_tma<<<tiles, kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_chunk_ids.p, h->d_rho.p, 0, g.nloc, h->nbp);
+                k_rho_tma<<<tiles, kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_chunk_ids.p, cmask, h->d_rho.p, 0, g.nloc, h->nbp);
             } else {
-                k_rho_tma<<<dim3(tiles, h->rho_split), kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_chunk_ids.p, h->d_rho_part.p,
+                k_rho_tma<<<dim3(tiles, h->rho_split), kRhoTmaThreads, kRhoTmaSmemBytes, st>>>(h->d_phi.p, h->d_P.p, h->d_chunk_ids.p, cmask, h->d_rho_part.p,
                                                                                           (long)h->rho_part_stride, g.nloc, h->nbp);
                 k_rho_combine<<<(unsigned)((g.nloc + 255) / 256), 256, 0, st>>>(h->d_rho_part.p, (long)h->rho_part_stride, h->rho_split, g.nloc, h->d_rho.p);
                 h->launches++;
@@ -901,8 +944,8 @@ void run_contract(dftgrid* h, int mode) {
         h->peer_used = true;
         h->launches++;
     }
-    k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, fock ? h->d_dF.p : h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p, h->d_pairs.p,
-                                                                     D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc);
+    k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, fock ? h->d_dF.p : h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p,
+                                                                     h->screened ? h->d_chunk_mask.p : nullptr, h->d_pairs.p, D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc);
     double* res = fock ? h->d_fres.p : h->d_res.p;
     if (h->peer_ready) {
         // split-K reduction straight into this rank's exchange buffer, then the cross-rank sum over peer memory
@@ -2045,6 +2088,13 @@ int dftgrid_scf_get_matrix(dftgrid_t* h, int which, double* out) {
         }
         CK(cudaStreamSynchronize(h->stream));
     });
+}
+
+int dftgrid_debug_screen_fraction(dftgrid_t* h, double* fraction) {
+    if (h->group) return dftgrid_debug_screen_fraction(h->group->subs[0], fraction);
+    if (!fraction) return 1;
+    *fraction = h->screened ? h->screen_work_fraction : 1.0;
+    return 0;
 }
 
 int dftgrid_debug_set_stress(dftgrid_t* h, int mode) {

@@ -85,22 +85,26 @@ constexpr int kLdK = kTileK + 4;    // 36
 constexpr int kLdN = kTileN + DFG_LDN_PAD;    // 132
 constexpr int kStages = 3;
 
-// flags[c] = 1 when any amplitude of the 32 rows of chunk c is non-zero.  Far from every nucleus exp(-alpha r^2)
-// underflows to exactly +0 (the outermost radial shells), and a chunk of exact zeros contributes exactly nothing to
-// rho, J or XC: the tensor kernels run over the list of non-zero chunks / tiles only.  Warp per chunk.
-__global__ void k_chunk_flags(const double* __restrict__ phi, long nchunk, int nbp, int* __restrict__ flags) {
+// Block-sparsity map of Phi (screening): mask[c] bit b = 1 when any amplitude of the 32 rows of chunk c
+// in the 32-column block b exceeds tau in magnitude.  Far from a nucleus exp(-alpha r^2) underflows to exactly +0 (the
+// outermost radial shells: whole chunks of exact zeros), and long before that a block's amplitudes are below any
+// threshold that could move rho, J or XC: a block with max |phi| <= tau contributes at most tau * |phi_other| * |d| per
+// point.  tau = 0 keeps the skipping exact; the default tau = 1e-20 (dftgrid_api.cu) is 10 orders of magnitude below the
+// 1e-10 parity tolerance of J / XC.  The tensor kernels skip, per 32-point chunk, the column blocks whose bit is clear:
+// whole pipeline stages when no warp needs them, otherwise per warp.  Warp per chunk; nbp / 32 <= 64 blocks.
+__global__ void k_chunk_masks(const double* __restrict__ phi, long nchunk, int nbp, double tau, unsigned long long* __restrict__ mask) {
     const long c = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= nchunk) return;
-    const double2* base = reinterpret_cast<const double2*>(phi + (size_t)c * kTileK * nbp);
-    const long n2 = (long)kTileK * nbp / 2;
-    bool nz = false;
-    for (long i = lane; i < n2; i += 32) {
-        const double2 v = base[i];
-        nz = nz || v.x != 0.0 || v.y != 0.0;
+    const double* base = phi + (size_t)c * kTileK * nbp;
+    unsigned long long m = 0ull;
+    for (int b = 0; b < nbp / 32; b++) {
+        double mx = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < kTileK; r++) mx = fmax(mx, fabs(base[(size_t)r * nbp + b * 32 + lane]));
+        if (__ballot_sync(0xffffffffu, mx > tau) != 0u) m |= 1ull << b;
     }
-    const unsigned any = __ballot_sync(0xffffffffu, nz);
-    if (lane == 0) flags[c] = any != 0u;
+    if (lane == 0) mask[c] = m;
 }
 
 // =========================================================================================================
@@ -153,6 +157,21 @@ __device__ __forceinline__ void rho_mma_stage(const double* st, double (&acc)[4]
 // Steps of one CTA: for slab J = 0.., first the k-chunks past the slab (ascending), then the slab's own chunks in
 // DESCENDING order: own chunk `rel` feeds the column blocks <= rel, so after that step block `rel` is complete, and the
 // chunk's Phi tile in shared memory holds exactly the amplitudes of that block's columns for the row-dot epilogue.
+// Screening: a step (slab, k-chunk kc) is dropped for the whole CTA when no row group of the tile needs it — a row group
+// needs it when its Phi block kc is significant (A operand) and it has a significant block inside the slab (it will use
+// T there); see k_chunk_masks.  Producer and DMMA warps evaluate the same predicate on the same four masks.
+struct RhoMasks {
+    unsigned long long m[4];
+    bool all;  // no map (more than 64 column blocks): every step is kept
+    __device__ __forceinline__ bool keep(int slab, int kc) const {
+        if (all) return true;
+        bool k = false;
+#pragma unroll
+        for (int r = 0; r < 4; r++) k = k || (((m[r] >> kc) & 1ull) && ((m[r] >> (4 * slab)) & 0xFull));
+        return k;
+    }
+};
+
 struct RhoStep {
     int slab, i, nbp, stride;  // a CTA visits the slabs slab, slab + stride, ... (stride = number of CTAs sharing a tile)
     __device__ __forceinline__ int nk() const { return nbp / kTileK; }
@@ -169,6 +188,11 @@ struct RhoStep {
             slab += stride;
         }
     }
+    __device__ __forceinline__ bool valid(int nslab) const { return slab < nslab; }
+    // move to the first kept step at or after the current one
+    __device__ __forceinline__ void seek(const RhoMasks& M, int nslab) {
+        while (valid(nslab) && !M.keep(slab, chunk())) advance();
+    }
 };
 
 // grid = (ceil(number of non-zero 32-point chunks / 4), nsplit): a CTA's 128-row tile is made of four non-zero chunks
@@ -180,8 +204,8 @@ struct RhoStep {
 // the producer warpgroup hands its share back (setmaxnreg.dec) and the DMMA warpgroups grow to 232 (setmaxnreg.inc), so
 // the 128-register accumulator tile plus fragments and loop state never spill.
 __global__ void __launch_bounds__(kRhoTmaThreads, 1)
-k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const int* __restrict__ chunk_ids, double* __restrict__ out, long part_stride,
-          long nloc, int nbp) {
+k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const int* __restrict__ chunk_ids,
+          const unsigned long long* __restrict__ chunk_mask, double* __restrict__ out, long part_stride, long nloc, int nbp) {
     extern __shared__ __align__(128) double sm[];
     double* red = sm + (size_t)kStages * kRhoStageDoubles;  // [2][128]
     unsigned long long* full = reinterpret_cast<unsigned long long*>(red + 2 * kTileM);
@@ -199,8 +223,13 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
     const int nk = nbp / kTileK;
     const int nslab = (nbp + kTileN - 1) / kTileN;
     const int sub = blockIdx.y, nsplit = gridDim.y;
-    int total = 0;
-    for (int J = sub; J < nslab; J += nsplit) total += nk - J * (kTileN / kTileK);
+    RhoMasks M;
+    M.all = chunk_mask == nullptr;
+#pragma unroll
+    for (int r = 0; r < 4; r++) M.m[r] = (!M.all && my_chunks[r] >= 0) ? chunk_mask[4 * (size_t)blockIdx.x + r] : 0ull;
+    int total = 0;  // kept steps of this CTA
+    for (int J = sub; J < nslab; J += nsplit)
+        for (int kc = J * (kTileN / kTileK); kc < nk; kc++) total += M.keep(J, kc) ? 1 : 0;
     double* rho = out + (size_t)sub * part_stride;
 
     if (warp >= 8) {
@@ -212,6 +241,7 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
         RhoStep ld{sub, 0, nbp, nsplit};
         const double* grp = phi + ((size_t)max(my_chunks[j], 0) * kTileK + lane) * (size_t)nbp;  // unused group: any valid rows
         for (int it = 0; it < total; it++) {
+            ld.seek(M, nslab);
             const unsigned stage = (unsigned)it % kStages, round = (unsigned)it / kStages;
             double* st = sm + (size_t)stage * kRhoStageDoubles;
             const int slab = ld.slab * kTileN, kc = ld.chunk() * kTileK;
@@ -239,18 +269,29 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
     double rowsum[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][8][2];
     RhoStep cs{sub, 0, nbp, nsplit};
+    // significant column blocks of this warp's 32 rows (selects, not a dynamically indexed register array)
+    const unsigned long long mymask = M.all ? ~0ull : (wm == 0 ? M.m[0] : wm == 1 ? M.m[1] : wm == 2 ? M.m[2] : M.m[3]);
+    auto mybit = [&](int b) { return M.all || ((mymask >> b) & 1ull); };
+    int cur_slab = -1;
     for (int it = 0; it < total; it++) {
+        cs.seek(M, nslab);
         const unsigned stage = (unsigned)it % kStages, round = (unsigned)it / kStages;
         const int nblk = cs.nblk();
-        if (cs.i == 0) {
+        if (cs.slab != cur_slab) {  // first kept step of a slab
+            cur_slab = cs.slab;
 #pragma unroll
             for (int mt = 0; mt < 4; mt++)
 #pragma unroll
                 for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
         }
-        // a chunk past the slab feeds every column block, the slab's own chunk `rel` the blocks <= rel
+        // a chunk past the slab feeds every column block, the slab's own chunk `rel` the blocks <= rel; a warp skips the
+        // step when its rows' amplitudes in k-block `chunk` are insignificant, and a column block whose amplitudes are
+        // (T there is only ever multiplied by them)
         const int rel = cs.rel();
-        const bool h0 = blk0 < nblk && (rel < 0 || blk0 <= rel), h1 = blk1 < nblk && (rel < 0 || blk1 <= rel);
+        const bool ka = mybit(cs.chunk());
+        const int sb = cs.slab * (kTileN / kTileK);
+        const bool h0 = ka && blk0 < nblk && (rel < 0 || blk0 <= rel) && mybit(sb + blk0);
+        const bool h1 = ka && blk1 < nblk && (rel < 0 || blk1 <= rel) && mybit(sb + blk1);
         mbar_wait(full + stage, round & 1u);
         stress_delay(2, (unsigned)it);
         const double* st = sm + (size_t)stage * kRhoStageDoubles;
@@ -260,7 +301,7 @@ k_rho_tma(const double* __restrict__ phi, const double* __restrict__ Ph, const i
             rho_mma_stage<true, false>(st, acc, wm, blk0 * 32, blk1 * 32, lane);
         else if (h1)
             rho_mma_stage<false, true>(st, acc, wm, blk0 * 32, blk1 * 32, lane);
-        if (rel >= 0 && (rel == blk0 || rel == blk1)) {
+        if (rel >= 0 && (rel == blk0 || rel == blk1) && mybit(sb + rel)) {
             // block `rel` is complete: rowsum += T''[p][n] * Phi[p][n] with Phi[p][slab + 32 rel ..] = this stage's Phi tile
             const double* As = st + (wm * 32 + g) * kLdK + q * 2;
             if (rel == blk0) {
@@ -316,7 +357,8 @@ __global__ void k_rho_combine(const double* __restrict__ part, long part_stride,
 // =========================================================================================================
 // C_z = Phi^T diag(d_z) Phi  (upper-triangular 128x128 tile pairs, split over point ranges)
 // =========================================================================================================
-constexpr int kConStageDoubles = 2 * kTileK * kLdN + kTileK;
+constexpr int kConMaskOff = 2 * kTileK * kLdN + kTileK;  // 8-byte slot after the weights: the staged chunk's block map
+constexpr int kConStageDoubles = kConMaskOff + 2;         // (+2 keeps every stage 16-byte aligned for the bulk copies)
 
 // Warp tiling of the 128 x (128|64) output tile: 8 warps stacked along M, each owning MT = 2 row tiles (16 rows) and
 // the whole width (NT = 16 column tiles, 8 for an edge tile).  Per k4-step a warp then scales only 2 A fragments by the
@@ -342,6 +384,34 @@ __device__ __forceinline__ void con_mma_stage(const double* st, double (&acc)[32
     }
 }
 
+
+// The same when some of the tile's 32-column blocks are insignificant for this chunk (screening, k_chunk_masks): bbits bit
+// g = column tiles 4g .. 4g+3 are needed.  Warp-uniform branches around groups of static DMMAs.
+template <int MT, int NT>
+__device__ __forceinline__ void con_mma_stage_masked(const double* st, double (&acc)[32][2], int warp, int lane, unsigned bbits) {
+    const double* As = st;
+    const double* Bs = st + kTileK * kLdN;
+    const double* ds = st + 2 * kTileK * kLdN;
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < kTileK; kk += 4) {
+        double a[MT];
+        const double dv = ds[kk + q];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) a[mt] = As[(kk + q) * kLdN + warp * (MT * 8) + mt * 8 + g] * dv;
+#pragma unroll
+        for (int grp = 0; grp < NT / 4; grp++)
+            if ((bbits >> grp) & 1u) {
+                double b[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) b[t] = Bs[(kk + q) * kLdN + (grp * 4 + t) * 8 + g];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int t = 0; t < 4; t++) dmma884(acc[mt * NT + grp * 4 + t][0], acc[mt * NT + grp * 4 + t][1], a[mt], b[t]);
+            }
+    }
+}
 
 // Diagonal tile pair (ti == tj), full 128 wide: only the 8x8 DMMA tiles on or above the diagonal are needed.  Warp W
 // owns row tile W (against column tiles W..15) and row tile 15-W (against column tiles 15-W..15): 17 DMMAs per
@@ -370,6 +440,30 @@ __device__ __forceinline__ void con_mma_stage_tri(const double* st, double (&acc
     }
 }
 
+
+// Diagonal tile with insignificant 32-column blocks (bits: one per block of the tile, rows and columns alike).
+template <int W>
+__device__ __forceinline__ void con_mma_stage_tri_masked(const double* st, double (&acc)[32][2], int lane, unsigned bits) {
+    const double* As = st;
+    const double* ds = st + 2 * kTileK * kLdN;
+    const int g = lane >> 2, q = lane & 3;
+    constexpr int NB = 16 - W;
+    const bool r0 = (bits >> (W / 4)) & 1u, r1 = (bits >> ((15 - W) / 4)) & 1u;
+    if (!r0 && !r1) return;
+#pragma unroll
+    for (int kk = 0; kk < kTileK; kk += 4) {
+        const double dv = ds[kk + q];
+        const double a0 = As[(kk + q) * kLdN + W * 8 + g] * dv;
+        const double a1 = As[(kk + q) * kLdN + (15 - W) * 8 + g] * dv;
+#pragma unroll
+        for (int c = 0; c < NB; c++)
+            if ((bits >> ((W + c) / 4)) & 1u) {
+                const double b = As[(kk + q) * kLdN + (W + c) * 8 + g];
+                if (r0) dmma884(acc[c][0], acc[c][1], a0, b);
+                if (W + c >= 15 - W && r1) dmma884(acc[NB + (W + c) - (15 - W)][0], acc[NB + (W + c) - (15 - W)][1], a1, b);
+            }
+    }
+}
 
 // 64-wide diagonal edge tile: warp w owns row tile w against the 8 column tiles (the tile is 1 of ~28 pairs).
 __device__ __forceinline__ void con_mma_stage_diag_edge(const double* st, double (&acc)[32][2], int warp, int lane) {
@@ -405,22 +499,28 @@ struct ConSeg {
     unsigned tb, te;  // [tb, te) in units of 2^-31
 };
 
-__device__ __forceinline__ bool con_owns(const ConSeg& sg, int x) {
+// Screening (k_chunk_masks): a chunk whose amplitudes are insignificant in ALL of tile i's column blocks, or in all of
+// tile j's, contributes nothing to the pair and is not staged at all: ownership = hash range AND both tiles significant.
+// mi / mj: the tiles' block bits inside a chunk map; cm: the chunk's map (all ones without a map).
+__device__ __forceinline__ bool con_owns(const ConSeg& sg, int x, unsigned long long cm, unsigned long long mi, unsigned long long mj) {
     const unsigned u = ((unsigned)x * 2654435769u) >> 1;
-    return u >= sg.tb && u < sg.te;
+    return u >= sg.tb && u < sg.te && (cm & mi) != 0ull && (cm & mj) != 0ull;
 }
+__device__ __forceinline__ unsigned long long con_tile_bits(int t) { return 0xFull << (4 * t); }
 
 // Number of chunk positions of [x0, x1) owned by the segment (warp-collective, same value in every lane).
-__device__ __forceinline__ int con_count_owned(const ConSeg& sg, int x0, int x1, int lane) {
+__device__ __forceinline__ int con_count_owned(const ConSeg& sg, int x0, int x1, int lane, const unsigned long long* __restrict__ chunk_mask,
+                                               unsigned long long mi, unsigned long long mj) {
     int cnt = 0;
     for (int base = x0; base < x1; base += 32) {
         const int x = base + lane;
-        cnt += __popc(__ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x)));
+        const unsigned long long cm = (x < x1 && chunk_mask) ? chunk_mask[x] : ~0ull;
+        cnt += __popc(__ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x, cm, mi, mj)));
     }
     return cnt;
 }
 
-constexpr int kConTmaThreads = kDenseThreads + 32;
+constexpr int kConTmaThreads = kDenseThreads + 128;  // 2 DMMA warpgroups + 1 producer warpgroup (its first warp produces)
 constexpr size_t kConTmaSmemBytes = (size_t)kStages * kConStageDoubles * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
 
 // The chunk loop of one segment for one DMMA warp; `op` consumes one staged chunk.
@@ -439,8 +539,16 @@ __device__ __forceinline__ void con_run_segment(const double* sm, unsigned long 
 
 // Accumulator tile layouts of the four segment kinds: how the DMMA stage, the store to and the reload from the
 // segment's partial tile address the 32 accumulator pairs.
+// abits / bbits: significance of the four 32-column blocks of tile i (the A rows; warp w's rows lie in block w / 2) and of
+// tile j for the staged chunk.
 struct ConModeFull {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 16>(st, acc, warp, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned bbits) {
+        if (!((abits >> (warp >> 1)) & 1u)) return;
+        if (bbits == 0xFu)
+            con_mma_stage<2, 16>(st, acc, warp, lane);
+        else
+            con_mma_stage_masked<2, 16>(st, acc, warp, lane, bbits);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -460,7 +568,13 @@ struct ConModeFull {
     }
 };
 struct ConModeNarrow {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 8>(st, acc, warp, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned bbits) {
+        if (!((abits >> (warp >> 1)) & 1u)) return;
+        if ((bbits & 3u) == 3u)
+            con_mma_stage<2, 8>(st, acc, warp, lane);
+        else
+            con_mma_stage_masked<2, 8>(st, acc, warp, lane, bbits);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -479,9 +593,27 @@ struct ConModeNarrow {
             }
     }
 };
+// 64-wide diagonal edge tile with only some column blocks significant (bits 0, 1)
+__device__ __forceinline__ void con_mma_stage_diag_edge_half(const double* st, double (&acc)[32][2], int warp, int lane, unsigned bits) {
+    const double* As = st;
+    const double* ds = st + 2 * kTileK * kLdN;
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < kTileK; kk += 4) {
+        const double dv = ds[kk + q];
+        const double a0 = As[(kk + q) * kLdN + warp * 8 + g] * dv;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+            if ((bits >> (nt >> 2)) & 1u) dmma884(acc[nt][0], acc[nt][1], a0, As[(kk + q) * kLdN + nt * 8 + g]);
+    }
+}
+
 // 32-wide edge tile (nbp = 128 k + 32, e.g. nb = 524): 4 column tiles instead of 8
 struct ConModeNarrow32 {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 4>(st, acc, warp, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned bbits) {
+        if (!((abits >> (warp >> 1)) & 1u) || !(bbits & 1u)) return;
+        con_mma_stage<2, 4>(st, acc, warp, lane);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -502,8 +634,8 @@ struct ConModeNarrow32 {
 };
 // 32-wide diagonal edge tile: warps 0-3 own row tile w against the 4 column tiles, warps 4-7 only follow the pipeline
 struct ConModeDiagEdge32 {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) {
-        if (warp >= 4) return;
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned) {
+        if (warp >= 4 || !(abits & 1u)) return;
         const double* As = st;
         const double* ds = st + 2 * kTileK * kLdN;
         const int g = lane >> 2, q = lane & 3;
@@ -536,7 +668,13 @@ struct ConModeDiagEdge32 {
     }
 };
 struct ConModeDiagEdge {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage_diag_edge(st, acc, warp, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned) {
+        if (!((abits >> (warp >> 2)) & 1u)) return;  // row tile w lies in block w / 4
+        if ((abits & 3u) == 3u)
+            con_mma_stage_diag_edge(st, acc, warp, lane);
+        else  // one of the two column blocks is insignificant: this warp's own block, so the other block cannot be reached here
+            con_mma_stage_diag_edge_half(st, acc, warp, lane, abits);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -555,7 +693,12 @@ struct ConModeDiagEdge {
 };
 template <int W>
 struct ConModeTri {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int, int lane) { con_mma_stage_tri<W>(st, acc, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int, int lane, unsigned abits, unsigned) {
+        if (abits == 0xFu)
+            con_mma_stage_tri<W>(st, acc, lane);
+        else
+            con_mma_stage_tri_masked<W>(st, acc, lane, abits);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -590,7 +733,7 @@ struct ConModeTri {
 template <class Mode>
 __device__ __forceinline__ void con_segment_blocks_mode(const double* sm, unsigned long long* full, unsigned long long* empty, unsigned& n, int warp,
                                                         int lane, const ConSeg& sg, double* out, int nchunk, int bc, int b_begin, int b_end,
-                                                        bool fresh) {
+                                                        bool fresh, const unsigned long long* __restrict__ chunk_mask, int ti, int tj) {
     double acc[32][2];
     if (fresh) {
 #pragma unroll
@@ -600,19 +743,23 @@ __device__ __forceinline__ void con_segment_blocks_mode(const double* sm, unsign
     }
     {
         const int x0 = min(b_begin * bc, nchunk), x1 = min(b_end * bc, nchunk);
-        con_run_segment(sm, full, empty, con_count_owned(sg, x0, x1, lane), n, lane, [&](const double* st) { Mode::mma(st, acc, warp, lane); });
+        con_run_segment(sm, full, empty, con_count_owned(sg, x0, x1, lane, chunk_mask, con_tile_bits(ti), con_tile_bits(tj)), n, lane,
+                        [&](const double* st) {
+                            const unsigned long long cm = *reinterpret_cast<const unsigned long long*>(st + kConMaskOff);
+                            Mode::mma(st, acc, warp, lane, (unsigned)(cm >> (4 * ti)) & 0xFu, (unsigned)(cm >> (4 * tj)) & 0xFu);
+                        });
     }
     Mode::template io<false>(out, acc, warp, lane);
 }
 
 __device__ __forceinline__ void con_segment_blocks(const double* sm, unsigned long long* full, unsigned long long* empty, unsigned& n, int warp, int lane,
                                                    const ConSeg sg, const int* __restrict__ pair_ij, double* out, int nbp, int nchunk, int bc,
-                                                   int b_begin, int b_end, bool fresh) {
+                                                   int b_begin, int b_end, bool fresh, const unsigned long long* __restrict__ chunk_mask) {
     const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
     const bool diag = ti == tj;
     const int wj = min(kTileN, nbp - tj * kTileN);
     const bool narrow = wj <= 64, narrow32 = wj <= 32;
-#define DFG_SEG_ARGS sm, full, empty, n, warp, lane, sg, out, nchunk, bc, b_begin, b_end, fresh
+#define DFG_SEG_ARGS sm, full, empty, n, warp, lane, sg, out, nchunk, bc, b_begin, b_end, fresh, chunk_mask, ti, tj
     if (!diag) {
         if (narrow32)
             con_segment_blocks_mode<ConModeNarrow32>(DFG_SEG_ARGS);
@@ -644,8 +791,8 @@ __device__ __forceinline__ void con_segment_blocks(const double* sm, unsigned lo
 // nchunk = number of non-zero chunks (length of chunk_ids), bc = chunks per L2 block.
 __global__ void __launch_bounds__(kConTmaThreads, 1)
 k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, const double* __restrict__ d1, const int* __restrict__ chunk_ids,
-               const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs, const int* __restrict__ cta_seg_off,
-               double* __restrict__ partial, int nbp, int nchunk, int bc) {
+               const unsigned long long* __restrict__ chunk_mask, const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs,
+               const int* __restrict__ cta_seg_off, double* __restrict__ partial, int nbp, int nchunk, int bc) {
     extern __shared__ __align__(128) double sm[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)kStages * kConStageDoubles);
     unsigned long long* empty = full + kStages;
@@ -661,7 +808,11 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
     const int s_begin = cta_seg_off[blockIdx.x], s_end = cta_seg_off[blockIdx.x + 1];
     const int nblock = bc > 0 ? (nchunk + bc - 1) / bc : 0;
     unsigned n = 0;  // running stage counter, continues across segments and blocks
-    if (warp == 8) {
+    // 384 threads start with 168 registers each; the producer warpgroup hands registers back and the DMMA warpgroups grow,
+    // so the 64-register accumulator tile, the fragments and the screening state never spill (as in k_rho_tma)
+    if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+        if (warp > 8) return;
         // ===== producer warp: one 1 KB Phi row (per operand) per lane and stage; block-major, like the consumers =====
         for (int b = 0; b < nblock; b++) {
             for (int sidx = s_begin; sidx < s_end; sidx++) {
@@ -673,19 +824,26 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
                 const unsigned wi = (unsigned)min(kTileM, nbp - ci) * 8u, wj = (unsigned)min(kTileN, nbp - cj) * 8u;  // valid row bytes
                 const unsigned bytes = kTileK * (wi + (diag ? 0u : wj)) + kTileK * 8u;
                 const int x0 = min(b * bc, nchunk), x1 = min((b + 1) * bc, nchunk);
+                const unsigned long long mi = con_tile_bits(ti), mj = con_tile_bits(tj);
                 for (int base = x0; base < x1; base += 32) {
                     const int x = base + lane;
-                    unsigned mask = __ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x));
+                    const unsigned long long cm = (x < x1 && chunk_mask) ? chunk_mask[x] : ~0ull;
+                    unsigned mask = __ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x, cm, mi, mj));
                     const int my_chunk = x < x1 ? chunk_ids[x] : 0;
                     while (mask) {
                         const int src = __ffs(mask) - 1;
                         mask &= mask - 1u;
                         const size_t row0 = (size_t)__shfl_sync(0xffffffffu, my_chunk, src) * kTileK;
+                        const unsigned long long cmx = __shfl_sync(0xffffffffu, cm, src);
                         const unsigned stage = n % kStages, round = n / kStages;
                         double* st = sm + (size_t)stage * kConStageDoubles;
                         stress_delay(1, n);
                         mbar_wait(empty + stage, (round & 1u) ^ 1u);
-                        if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes);
+                        if (lane == 0) {
+                            // the chunk's block map travels with the stage (plain store, released by the arrive below)
+                            *reinterpret_cast<unsigned long long*>(st + kConMaskOff) = cmx;
+                            mbar_arrive_expect_tx(full + stage, bytes);
+                        }
                         __syncwarp();
                         const double* row = phi + (row0 + lane) * (size_t)nbp;
                         bulk_copy_g2s(st + lane * kLdN, row + ci, wi, full + stage);
@@ -699,22 +857,23 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
         return;
     }
     // ===== DMMA warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
     // A CTA with a single segment keeps its accumulators in registers while the blocks go by.  A CTA whose share crosses
     // an item boundary (2-3 segments) visits its segments in turn inside every block and parks the accumulators of the
     // inactive ones in their partial tiles (L2-resident) in between.
     const int nseg = s_end - s_begin;
     if (nseg == 1) {
         con_segment_blocks(sm, full, empty, n, warp, lane, segs[s_begin], pair_ij, partial + (size_t)s_begin * (size_t)(kTileM * kTileN), nbp, nchunk, bc,
-                           0, nblock, true);
+                           0, nblock, true, chunk_mask);
     } else {
         for (int b = 0; b < nblock; b++)
             for (int sidx = s_begin; sidx < s_end; sidx++)
                 con_segment_blocks(sm, full, empty, n, warp, lane, segs[sidx], pair_ij, partial + (size_t)sidx * (size_t)(kTileM * kTileN), nbp, nchunk,
-                                   bc, b, b + 1, b == 0);
+                                   bc, b, b + 1, b == 0, chunk_mask);
         if (nblock == 0)  // empty shard: the reduction still reads every segment's tile
             for (int sidx = s_begin; sidx < s_end; sidx++)
                 con_segment_blocks(sm, full, empty, n, warp, lane, segs[sidx], pair_ij, partial + (size_t)sidx * (size_t)(kTileM * kTileN), nbp, nchunk,
-                                   bc, 0, 0, true);
+                                   bc, 0, 0, true, chunk_mask);
     }
 }
 

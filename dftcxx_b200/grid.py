@@ -280,6 +280,13 @@ class MolecularGrid:
         self._ck(lib().dftgrid_scf_get_matrix(self.h, {"P": 0, "F_grid": 1, "F_prime": 2, "D_prime": 3}[which], _ptr(out)))
         return out
 
+    def screen_fraction(self):
+        """Mean fraction of a full contraction stage's tensor work left after screening (1.0 = nothing skipped)."""
+        f = C.c_double()
+        lib().dftgrid_debug_screen_fraction.argtypes = [C.c_void_p, _dp]
+        self._ck(lib().dftgrid_debug_screen_fraction(self.h, C.cast(C.byref(f), _dp)))
+        return f.value
+
     def debug_set_stress(self, mode):
         """Test hook: random delays in the producer (1) / consumer (2) warps of the tensor kernels' pipelines."""
         self._ck(lib().dftgrid_debug_set_stress(self.h, int(mode)))

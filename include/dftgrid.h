@@ -198,6 +198,11 @@ int dftgrid_debug_contract_schedule(int nbp, long nchunk, int nsm, int max_segs,
 int dftgrid_debug_contract_schedule_nz(int nbp, long nchunk, int nsm, int nz, int max_segs, int* segs_out, int* cta_off_out, int* nctas,
                                        int* nsegs, int* block_chunks);
 
+/* Screening statistics of the built grid: the mean fraction of a full contraction stage's tensor work that a chunk costs a
+ * tile pair under the block map of Phi (1 = nothing skipped; see csrc/kernels_dense.cuh k_chunk_masks).  The threshold on
+ * |phi| is 1e-20 unless the developer switch DFTGRID_SCREEN_TAU says otherwise (0 = exact zeros only, negative = off). */
+int dftgrid_debug_screen_fraction(dftgrid_t* h, double* fraction);
+
 /* Test hook: perturb the timing of the producer (bit 0) / consumer (bit 1) warps of the two tensor kernels' mbarrier
  * pipelines with pseudo-random delays on this handle's device(s); results must not change by a bit.  0 = off (default). */
 int dftgrid_debug_set_stress(dftgrid_t* h, int mode);
