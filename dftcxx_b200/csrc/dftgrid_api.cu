@@ -493,7 +493,9 @@ void build_active_lists(dftgrid* h, int nsm) {
             h->d_rho_part.zero(st);  // skipped (all-zero) chunks are never written
         }
     }
-    build_contract_schedule(h, h->n_active_chunks, nsm, item_frac.empty() ? nullptr : &item_frac);
+    // (the contraction itself is not screened: per-chunk skipping breaks the lockstep sweep its L2 sharing rests on — measured:
+    // DRAM reads 6.5 -> 18 GB, 12.3 -> 17.1 ms — so its schedule keeps the plain per-item costs; the fraction is reported only)
+    build_contract_schedule(h, h->n_active_chunks, nsm, nullptr);
 }
 
 // Sort the (local point, source atom) pairs of the cross-atom interpolation into (atom, spline interval) bins.
@@ -944,8 +946,8 @@ void run_contract(dftgrid* h, int mode) {
         h->peer_used = true;
         h->launches++;
     }
-    k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, fock ? h->d_dF.p : h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p,
-                                                                     h->screened ? h->d_chunk_mask.p : nullptr, h->d_pairs.p, D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc);
+    k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, fock ? h->d_dF.p : h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p, h->d_pairs.p,
+                                                                     D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc);
     double* res = fock ? h->d_fres.p : h->d_res.p;
     if (h->peer_ready) {
         // split-K reduction straight into this rank's exchange buffer, then the cross-rank sum over peer memory
@@ -2100,6 +2102,9 @@ int dftgrid_debug_screen_fraction(dftgrid_t* h, double* fraction) {
 int dftgrid_debug_set_stress(dftgrid_t* h, int mode) {
     GROUP_FORWARD(h, dftgrid_debug_set_stress(s, mode));
     return guarded([&] {
+#ifndef DFG_STRESS
+        if (mode != 0) throw std::runtime_error("this build has no stress hook (build libdftgrid_stress.so with -DDFG_STRESS)");
+#endif
         use_device(h);
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaMemcpyToSymbol(c_stress_mode, &mode, sizeof mode));

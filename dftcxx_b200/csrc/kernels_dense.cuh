@@ -62,9 +62,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
 // Test hook (dftgrid_debug_set_stress): pseudo-random delays in the producer (bit 0) and / or consumer (bit 1) warps of the
 // two mbarrier pipelines.  Any ordering bug between the bulk copies and the fragment loads (a stage overwritten before its
 // last reader, a stage read before its bytes landed) shows up as changed bits under the perturbed timing; the results must
-// stay identical to the unperturbed run (tests/test_gpu_stress.py).  Zero in production: one uniform constant load per stage.
+// stay identical to the unperturbed run (tests/test_gpu_stress.py).  Compiled only into libdftgrid_stress.so (-DDFG_STRESS):
+// even an untaken branch on a constant costs the contraction 3-5 % (measured 11.2 -> 11.6 ms), so the product has none.
 __constant__ int c_stress_mode = 0;
 __device__ __forceinline__ void stress_delay(int bit, unsigned n) {
+#ifdef DFG_STRESS
     if (c_stress_mode & bit) {
         unsigned h = (n * 2654435761u) ^ (blockIdx.x * 40503u) ^ ((threadIdx.x >> 5) * 9176u);
         h ^= h >> 13;
@@ -72,6 +74,7 @@ __device__ __forceinline__ void stress_delay(int bit, unsigned n) {
         h ^= h >> 15;
         if ((h & 3u) == 0u) __nanosleep(h % 3000u);
     }
+#endif
 }
 
 constexpr int kDenseThreads = 256;  // 8 DMMA warps
@@ -357,8 +360,7 @@ __global__ void k_rho_combine(const double* __restrict__ part, long part_stride,
 // =========================================================================================================
 // C_z = Phi^T diag(d_z) Phi  (upper-triangular 128x128 tile pairs, split over point ranges)
 // =========================================================================================================
-constexpr int kConMaskOff = 2 * kTileK * kLdN + kTileK;  // 8-byte slot after the weights: the staged chunk's block map
-constexpr int kConStageDoubles = kConMaskOff + 2;         // (+2 keeps every stage 16-byte aligned for the bulk copies)
+constexpr int kConStageDoubles = 2 * kTileK * kLdN + kTileK;
 
 // Warp tiling of the 128 x (128|64) output tile: 8 warps stacked along M, each owning MT = 2 row tiles (16 rows) and
 // the whole width (NT = 16 column tiles, 8 for an edge tile).  Per k4-step a warp then scales only 2 A fragments by the
@@ -384,34 +386,6 @@ __device__ __forceinline__ void con_mma_stage(const double* st, double (&acc)[32
     }
 }
 
-
-// The same when some of the tile's 32-column blocks are insignificant for this chunk (screening, k_chunk_masks): bbits bit
-// g = column tiles 4g .. 4g+3 are needed.  Warp-uniform branches around groups of static DMMAs.
-template <int MT, int NT>
-__device__ __forceinline__ void con_mma_stage_masked(const double* st, double (&acc)[32][2], int warp, int lane, unsigned bbits) {
-    const double* As = st;
-    const double* Bs = st + kTileK * kLdN;
-    const double* ds = st + 2 * kTileK * kLdN;
-    const int g = lane >> 2, q = lane & 3;
-#pragma unroll
-    for (int kk = 0; kk < kTileK; kk += 4) {
-        double a[MT];
-        const double dv = ds[kk + q];
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) a[mt] = As[(kk + q) * kLdN + warp * (MT * 8) + mt * 8 + g] * dv;
-#pragma unroll
-        for (int grp = 0; grp < NT / 4; grp++)
-            if ((bbits >> grp) & 1u) {
-                double b[4];
-#pragma unroll
-                for (int t = 0; t < 4; t++) b[t] = Bs[(kk + q) * kLdN + (grp * 4 + t) * 8 + g];
-#pragma unroll
-                for (int mt = 0; mt < MT; mt++)
-#pragma unroll
-                    for (int t = 0; t < 4; t++) dmma884(acc[mt * NT + grp * 4 + t][0], acc[mt * NT + grp * 4 + t][1], a[mt], b[t]);
-            }
-    }
-}
 
 // Diagonal tile pair (ti == tj), full 128 wide: only the 8x8 DMMA tiles on or above the diagonal are needed.  Warp W
 // owns row tile W (against column tiles W..15) and row tile 15-W (against column tiles 15-W..15): 17 DMMAs per
@@ -440,30 +414,6 @@ __device__ __forceinline__ void con_mma_stage_tri(const double* st, double (&acc
     }
 }
 
-
-// Diagonal tile with insignificant 32-column blocks (bits: one per block of the tile, rows and columns alike).
-template <int W>
-__device__ __forceinline__ void con_mma_stage_tri_masked(const double* st, double (&acc)[32][2], int lane, unsigned bits) {
-    const double* As = st;
-    const double* ds = st + 2 * kTileK * kLdN;
-    const int g = lane >> 2, q = lane & 3;
-    constexpr int NB = 16 - W;
-    const bool r0 = (bits >> (W / 4)) & 1u, r1 = (bits >> ((15 - W) / 4)) & 1u;
-    if (!r0 && !r1) return;
-#pragma unroll
-    for (int kk = 0; kk < kTileK; kk += 4) {
-        const double dv = ds[kk + q];
-        const double a0 = As[(kk + q) * kLdN + W * 8 + g] * dv;
-        const double a1 = As[(kk + q) * kLdN + (15 - W) * 8 + g] * dv;
-#pragma unroll
-        for (int c = 0; c < NB; c++)
-            if ((bits >> ((W + c) / 4)) & 1u) {
-                const double b = As[(kk + q) * kLdN + (W + c) * 8 + g];
-                if (r0) dmma884(acc[c][0], acc[c][1], a0, b);
-                if (W + c >= 15 - W && r1) dmma884(acc[NB + (W + c) - (15 - W)][0], acc[NB + (W + c) - (15 - W)][1], a1, b);
-            }
-    }
-}
 
 // 64-wide diagonal edge tile: warp w owns row tile w against the 8 column tiles (the tile is 1 of ~28 pairs).
 __device__ __forceinline__ void con_mma_stage_diag_edge(const double* st, double (&acc)[32][2], int warp, int lane) {
@@ -499,28 +449,22 @@ struct ConSeg {
     unsigned tb, te;  // [tb, te) in units of 2^-31
 };
 
-// Screening (k_chunk_masks): a chunk whose amplitudes are insignificant in ALL of tile i's column blocks, or in all of
-// tile j's, contributes nothing to the pair and is not staged at all: ownership = hash range AND both tiles significant.
-// mi / mj: the tiles' block bits inside a chunk map; cm: the chunk's map (all ones without a map).
-__device__ __forceinline__ bool con_owns(const ConSeg& sg, int x, unsigned long long cm, unsigned long long mi, unsigned long long mj) {
+__device__ __forceinline__ bool con_owns(const ConSeg& sg, int x) {
     const unsigned u = ((unsigned)x * 2654435769u) >> 1;
-    return u >= sg.tb && u < sg.te && (cm & mi) != 0ull && (cm & mj) != 0ull;
+    return u >= sg.tb && u < sg.te;
 }
-__device__ __forceinline__ unsigned long long con_tile_bits(int t) { return 0xFull << (4 * t); }
 
 // Number of chunk positions of [x0, x1) owned by the segment (warp-collective, same value in every lane).
-__device__ __forceinline__ int con_count_owned(const ConSeg& sg, int x0, int x1, int lane, const unsigned long long* __restrict__ chunk_mask,
-                                               unsigned long long mi, unsigned long long mj) {
+__device__ __forceinline__ int con_count_owned(const ConSeg& sg, int x0, int x1, int lane) {
     int cnt = 0;
     for (int base = x0; base < x1; base += 32) {
         const int x = base + lane;
-        const unsigned long long cm = (x < x1 && chunk_mask) ? chunk_mask[x] : ~0ull;
-        cnt += __popc(__ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x, cm, mi, mj)));
+        cnt += __popc(__ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x)));
     }
     return cnt;
 }
 
-constexpr int kConTmaThreads = kDenseThreads + 128;  // 2 DMMA warpgroups + 1 producer warpgroup (its first warp produces)
+constexpr int kConTmaThreads = kDenseThreads + 32;
 constexpr size_t kConTmaSmemBytes = (size_t)kStages * kConStageDoubles * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
 
 // The chunk loop of one segment for one DMMA warp; `op` consumes one staged chunk.
@@ -539,16 +483,8 @@ __device__ __forceinline__ void con_run_segment(const double* sm, unsigned long 
 
 // Accumulator tile layouts of the four segment kinds: how the DMMA stage, the store to and the reload from the
 // segment's partial tile address the 32 accumulator pairs.
-// abits / bbits: significance of the four 32-column blocks of tile i (the A rows; warp w's rows lie in block w / 2) and of
-// tile j for the staged chunk.
 struct ConModeFull {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned bbits) {
-        if (!((abits >> (warp >> 1)) & 1u)) return;
-        if (bbits == 0xFu)
-            con_mma_stage<2, 16>(st, acc, warp, lane);
-        else
-            con_mma_stage_masked<2, 16>(st, acc, warp, lane, bbits);
-    }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 16>(st, acc, warp, lane); }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -568,13 +504,7 @@ struct ConModeFull {
     }
 };
 struct ConModeNarrow {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned bbits) {
-        if (!((abits >> (warp >> 1)) & 1u)) return;
-        if ((bbits & 3u) == 3u)
-            con_mma_stage<2, 8>(st, acc, warp, lane);
-        else
-            con_mma_stage_masked<2, 8>(st, acc, warp, lane, bbits);
-    }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 8>(st, acc, warp, lane); }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -593,27 +523,9 @@ struct ConModeNarrow {
             }
     }
 };
-// 64-wide diagonal edge tile with only some column blocks significant (bits 0, 1)
-__device__ __forceinline__ void con_mma_stage_diag_edge_half(const double* st, double (&acc)[32][2], int warp, int lane, unsigned bits) {
-    const double* As = st;
-    const double* ds = st + 2 * kTileK * kLdN;
-    const int g = lane >> 2, q = lane & 3;
-#pragma unroll
-    for (int kk = 0; kk < kTileK; kk += 4) {
-        const double dv = ds[kk + q];
-        const double a0 = As[(kk + q) * kLdN + warp * 8 + g] * dv;
-#pragma unroll
-        for (int nt = 0; nt < 8; nt++)
-            if ((bits >> (nt >> 2)) & 1u) dmma884(acc[nt][0], acc[nt][1], a0, As[(kk + q) * kLdN + nt * 8 + g]);
-    }
-}
-
 // 32-wide edge tile (nbp = 128 k + 32, e.g. nb = 524): 4 column tiles instead of 8
 struct ConModeNarrow32 {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned bbits) {
-        if (!((abits >> (warp >> 1)) & 1u) || !(bbits & 1u)) return;
-        con_mma_stage<2, 4>(st, acc, warp, lane);
-    }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 4>(st, acc, warp, lane); }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -634,8 +546,8 @@ struct ConModeNarrow32 {
 };
 // 32-wide diagonal edge tile: warps 0-3 own row tile w against the 4 column tiles, warps 4-7 only follow the pipeline
 struct ConModeDiagEdge32 {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned) {
-        if (warp >= 4 || !(abits & 1u)) return;
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) {
+        if (warp >= 4) return;
         const double* As = st;
         const double* ds = st + 2 * kTileK * kLdN;
         const int g = lane >> 2, q = lane & 3;
@@ -668,13 +580,7 @@ struct ConModeDiagEdge32 {
     }
 };
 struct ConModeDiagEdge {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned) {
-        if (!((abits >> (warp >> 2)) & 1u)) return;  // row tile w lies in block w / 4
-        if ((abits & 3u) == 3u)
-            con_mma_stage_diag_edge(st, acc, warp, lane);
-        else  // one of the two column blocks is insignificant: this warp's own block, so the other block cannot be reached here
-            con_mma_stage_diag_edge_half(st, acc, warp, lane, abits);
-    }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage_diag_edge(st, acc, warp, lane); }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -693,12 +599,7 @@ struct ConModeDiagEdge {
 };
 template <int W>
 struct ConModeTri {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int, int lane, unsigned abits, unsigned) {
-        if (abits == 0xFu)
-            con_mma_stage_tri<W>(st, acc, lane);
-        else
-            con_mma_stage_tri_masked<W>(st, acc, lane, abits);
-    }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int, int lane) { con_mma_stage_tri<W>(st, acc, lane); }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -733,7 +634,7 @@ struct ConModeTri {
 template <class Mode>
 __device__ __forceinline__ void con_segment_blocks_mode(const double* sm, unsigned long long* full, unsigned long long* empty, unsigned& n, int warp,
                                                         int lane, const ConSeg& sg, double* out, int nchunk, int bc, int b_begin, int b_end,
-                                                        bool fresh, const unsigned long long* __restrict__ chunk_mask, int ti, int tj) {
+                                                        bool fresh) {
     double acc[32][2];
     if (fresh) {
 #pragma unroll
@@ -743,23 +644,19 @@ __device__ __forceinline__ void con_segment_blocks_mode(const double* sm, unsign
     }
     {
         const int x0 = min(b_begin * bc, nchunk), x1 = min(b_end * bc, nchunk);
-        con_run_segment(sm, full, empty, con_count_owned(sg, x0, x1, lane, chunk_mask, con_tile_bits(ti), con_tile_bits(tj)), n, lane,
-                        [&](const double* st) {
-                            const unsigned long long cm = *reinterpret_cast<const unsigned long long*>(st + kConMaskOff);
-                            Mode::mma(st, acc, warp, lane, (unsigned)(cm >> (4 * ti)) & 0xFu, (unsigned)(cm >> (4 * tj)) & 0xFu);
-                        });
+        con_run_segment(sm, full, empty, con_count_owned(sg, x0, x1, lane), n, lane, [&](const double* st) { Mode::mma(st, acc, warp, lane); });
     }
     Mode::template io<false>(out, acc, warp, lane);
 }
 
 __device__ __forceinline__ void con_segment_blocks(const double* sm, unsigned long long* full, unsigned long long* empty, unsigned& n, int warp, int lane,
                                                    const ConSeg sg, const int* __restrict__ pair_ij, double* out, int nbp, int nchunk, int bc,
-                                                   int b_begin, int b_end, bool fresh, const unsigned long long* __restrict__ chunk_mask) {
+                                                   int b_begin, int b_end, bool fresh) {
     const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
     const bool diag = ti == tj;
     const int wj = min(kTileN, nbp - tj * kTileN);
     const bool narrow = wj <= 64, narrow32 = wj <= 32;
-#define DFG_SEG_ARGS sm, full, empty, n, warp, lane, sg, out, nchunk, bc, b_begin, b_end, fresh, chunk_mask, ti, tj
+#define DFG_SEG_ARGS sm, full, empty, n, warp, lane, sg, out, nchunk, bc, b_begin, b_end, fresh
     if (!diag) {
         if (narrow32)
             con_segment_blocks_mode<ConModeNarrow32>(DFG_SEG_ARGS);
@@ -791,8 +688,8 @@ __device__ __forceinline__ void con_segment_blocks(const double* sm, unsigned lo
 // nchunk = number of non-zero chunks (length of chunk_ids), bc = chunks per L2 block.
 __global__ void __launch_bounds__(kConTmaThreads, 1)
 k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, const double* __restrict__ d1, const int* __restrict__ chunk_ids,
-               const unsigned long long* __restrict__ chunk_mask, const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs,
-               const int* __restrict__ cta_seg_off, double* __restrict__ partial, int nbp, int nchunk, int bc) {
+               const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs, const int* __restrict__ cta_seg_off,
+               double* __restrict__ partial, int nbp, int nchunk, int bc) {
     extern __shared__ __align__(128) double sm[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)kStages * kConStageDoubles);
     unsigned long long* empty = full + kStages;
@@ -808,11 +705,7 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
     const int s_begin = cta_seg_off[blockIdx.x], s_end = cta_seg_off[blockIdx.x + 1];
     const int nblock = bc > 0 ? (nchunk + bc - 1) / bc : 0;
     unsigned n = 0;  // running stage counter, continues across segments and blocks
-    // 384 threads start with 168 registers each; the producer warpgroup hands registers back and the DMMA warpgroups grow,
-    // so the 64-register accumulator tile, the fragments and the screening state never spill (as in k_rho_tma)
-    if (warp >= 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
-        if (warp > 8) return;
+    if (warp == 8) {
         // ===== producer warp: one 1 KB Phi row (per operand) per lane and stage; block-major, like the consumers =====
         for (int b = 0; b < nblock; b++) {
             for (int sidx = s_begin; sidx < s_end; sidx++) {
@@ -824,26 +717,19 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
                 const unsigned wi = (unsigned)min(kTileM, nbp - ci) * 8u, wj = (unsigned)min(kTileN, nbp - cj) * 8u;  // valid row bytes
                 const unsigned bytes = kTileK * (wi + (diag ? 0u : wj)) + kTileK * 8u;
                 const int x0 = min(b * bc, nchunk), x1 = min((b + 1) * bc, nchunk);
-                const unsigned long long mi = con_tile_bits(ti), mj = con_tile_bits(tj);
                 for (int base = x0; base < x1; base += 32) {
                     const int x = base + lane;
-                    const unsigned long long cm = (x < x1 && chunk_mask) ? chunk_mask[x] : ~0ull;
-                    unsigned mask = __ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x, cm, mi, mj));
+                    unsigned mask = __ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x));
                     const int my_chunk = x < x1 ? chunk_ids[x] : 0;
                     while (mask) {
                         const int src = __ffs(mask) - 1;
                         mask &= mask - 1u;
                         const size_t row0 = (size_t)__shfl_sync(0xffffffffu, my_chunk, src) * kTileK;
-                        const unsigned long long cmx = __shfl_sync(0xffffffffu, cm, src);
                         const unsigned stage = n % kStages, round = n / kStages;
                         double* st = sm + (size_t)stage * kConStageDoubles;
                         stress_delay(1, n);
                         mbar_wait(empty + stage, (round & 1u) ^ 1u);
-                        if (lane == 0) {
-                            // the chunk's block map travels with the stage (plain store, released by the arrive below)
-                            *reinterpret_cast<unsigned long long*>(st + kConMaskOff) = cmx;
-                            mbar_arrive_expect_tx(full + stage, bytes);
-                        }
+                        if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes);
                         __syncwarp();
                         const double* row = phi + (row0 + lane) * (size_t)nbp;
                         bulk_copy_g2s(st + lane * kLdN, row + ci, wi, full + stage);
@@ -857,23 +743,22 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
         return;
     }
     // ===== DMMA warps =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
     // A CTA with a single segment keeps its accumulators in registers while the blocks go by.  A CTA whose share crosses
     // an item boundary (2-3 segments) visits its segments in turn inside every block and parks the accumulators of the
     // inactive ones in their partial tiles (L2-resident) in between.
     const int nseg = s_end - s_begin;
     if (nseg == 1) {
         con_segment_blocks(sm, full, empty, n, warp, lane, segs[s_begin], pair_ij, partial + (size_t)s_begin * (size_t)(kTileM * kTileN), nbp, nchunk, bc,
-                           0, nblock, true, chunk_mask);
+                           0, nblock, true);
     } else {
         for (int b = 0; b < nblock; b++)
             for (int sidx = s_begin; sidx < s_end; sidx++)
                 con_segment_blocks(sm, full, empty, n, warp, lane, segs[sidx], pair_ij, partial + (size_t)sidx * (size_t)(kTileM * kTileN), nbp, nchunk,
-                                   bc, b, b + 1, b == 0, chunk_mask);
+                                   bc, b, b + 1, b == 0);
         if (nblock == 0)  // empty shard: the reduction still reads every segment's tile
             for (int sidx = s_begin; sidx < s_end; sidx++)
                 con_segment_blocks(sm, full, empty, n, warp, lane, segs[sidx], pair_ij, partial + (size_t)sidx * (size_t)(kTileM * kTileN), nbp, nchunk,
-                                   bc, 0, 0, true, chunk_mask);
+                                   bc, 0, 0, true);
     }
 }
 

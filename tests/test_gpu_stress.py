@@ -1,8 +1,8 @@
 """Race evidence for the two warp-specialised tensor kernels (k_rho_tma, k_contract_tma).  compute-sanitizer's racecheck
 does not model mbarrier-ordered cp.async.bulk traffic (it reports the producer's writes against the DMMA warps' fragment
 loads), so two independent lines of evidence are kept in the suite instead:
- 1. timing perturbation: pseudo-random delays injected into the producer and / or consumer warps (dftgrid_debug_set_stress)
-    must not change a single bit of rho, J, XC, F — an ordering bug would;
+ 1. timing perturbation: pseudo-random delays injected into the producer and / or consumer warps (dftgrid_debug_set_stress,
+    compiled only into the test build libdftgrid_stress.so) must not change a single bit of rho, J, XC, F — an ordering bug would;
  2. compute-sanitizer --tool memcheck on a whole small iteration (out-of-bounds / misaligned bulk copies, bad peer pointers)."""
 import os
 import shutil
@@ -17,52 +17,75 @@ from common import ROOT, grid_params, load_golden, system_from_golden
 pytestmark = pytest.mark.gpu
 
 
+STRESS_LIB = os.path.join(ROOT, "dftcxx_b200", "libdftgrid_stress.so")
+
+WORKER = r"""
+import sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import numpy as np
+from common import grid_params, load_golden, system_from_golden
+from dftcxx_b200.grid import MolecularGrid
+from dftcxx_b200.systems import WORKLOADS, synthetic_density
+
+def check(mg, P, modes, reps):
+    J0, XC0, exc0, nel0 = mg.iteration(P)
+    rho0 = mg.get_densities()
+    F0, ej0, _, _ = mg.fock(P)
+    for mode in modes:
+        mg.debug_set_stress(mode)
+        for _ in range(reps):
+            J, XC, exc, nel = mg.iteration(P)
+            assert np.array_equal(J, J0) and np.array_equal(XC, XC0) and exc == exc0 and nel == nel0, mode
+            assert np.array_equal(mg.get_densities(), rho0), mode
+            F, ej, _, _ = mg.fock(P)
+            assert np.array_equal(F, F0) and ej == ej0, mode
+    mg.debug_set_stress(0)
+
+name = sys.argv[1]
+if name in WORKLOADS:
+    fac, prm = WORKLOADS[name]
+    mol = fac()
+    mg = MolecularGrid(mol); mg.set_grid_parameters(*prm); mg.create_grid()
+    check(mg, synthetic_density(mol), (3,), 1)
+else:
+    g = load_golden(name)
+    mg = MolecularGrid(system_from_golden(g)); mg.set_grid_parameters(*grid_params(g)); mg.create_grid()
+    check(mg, g["P"], (1, 2, 3), 2)
+mg.close()
+print("STRESS_OK", name)
+"""
+
+
+def run_worker(name):
+    if not os.path.exists(STRESS_LIB):
+        pytest.skip("libdftgrid_stress.so not built (make -C dftcxx_b200/csrc stress)")
+    code = WORKER % dict(root=ROOT, tests=os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code, name], capture_output=True, text=True, timeout=900, cwd=ROOT,
+                       env=dict(os.environ, DFTGRID_LIB=STRESS_LIB))
+    assert r.returncode == 0 and "STRESS_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+
+
 @pytest.mark.parametrize("name", ["benzene_p631_fine", "h2o8_p631_fine"])
 def test_pipeline_results_are_independent_of_producer_and_consumer_timing(name):
-    from dftcxx_b200.grid import MolecularGrid
-
-    g = load_golden(name)
-    mg = MolecularGrid(system_from_golden(g))
-    mg.set_grid_parameters(*grid_params(g))
-    mg.create_grid()
-    try:
-        P = g["P"]
-        J0, XC0, exc0, nel0 = mg.iteration(P)
-        rho0 = mg.get_densities()
-        F0, ej0, _, _ = mg.fock(P)
-        for mode in (1, 2, 3):
-            mg.debug_set_stress(mode)
-            for _ in range(2):
-                J, XC, exc, nel = mg.iteration(P)
-                assert np.array_equal(J, J0) and np.array_equal(XC, XC0) and exc == exc0 and nel == nel0, mode
-                assert np.array_equal(mg.get_densities(), rho0), mode
-                F, ej, _, _ = mg.fock(P)
-                assert np.array_equal(F, F0) and ej == ej0, mode
-        mg.debug_set_stress(0)
-    finally:
-        mg.close()
+    run_worker(name)
 
 
 def test_large_tiles_under_stress():
     """(H2O)32: nb = 416 = several tile pairs, an edge tile, multi-segment stream-K CTAs, three-stage pipelines running for
     thousands of stages per CTA."""
-    from dftcxx_b200.grid import MolecularGrid
-    from dftcxx_b200.systems import WORKLOADS, synthetic_density
+    run_worker("h2o32")
 
-    fac, prm = WORKLOADS["h2o32"]
-    mol = fac()
-    mg = MolecularGrid(mol)
-    mg.set_grid_parameters(*prm)
+
+def test_production_library_has_no_stress_hook():
+    from dftcxx_b200.grid import GridError, MolecularGrid
+
+    g = load_golden("h2o_sto3g")
+    mg = MolecularGrid(system_from_golden(g))
+    mg.set_grid_parameters(*grid_params(g))
     mg.create_grid()
     try:
-        P = synthetic_density(mol)
-        J0, XC0, exc0, nel0 = mg.iteration(P)
-        F0, ej0, _, _ = mg.fock(P)
-        mg.debug_set_stress(3)
-        J, XC, exc, nel = mg.iteration(P)
-        F, ej, _, _ = mg.fock(P)
-        mg.debug_set_stress(0)
-        assert np.array_equal(J, J0) and np.array_equal(XC, XC0) and exc == exc0 and np.array_equal(F, F0) and ej == ej0
+        with pytest.raises(GridError, match="no stress hook"):
+            mg.debug_set_stress(3)
     finally:
         mg.close()
 

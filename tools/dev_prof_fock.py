@@ -1,0 +1,21 @@
+"""Developer script: a few fused Fock builds of a workload (for ncu captures of the iteration kernels)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dftcxx_b200.grid import MolecularGrid
+from dftcxx_b200.systems import WORKLOADS, synthetic_density
+
+name = sys.argv[1] if len(sys.argv) > 1 else "h2o64"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+fac, prm = WORKLOADS[name]
+mol = fac()
+g = MolecularGrid(mol)
+g.set_grid_parameters(*prm)
+g.create_grid()
+P = synthetic_density(mol)
+os.environ["DFTGRID_NO_GRAPH"] = "1"
+for _ in range(n):
+    g.fock(P)
+print(g.timings(), "screen fraction", g.screen_fraction())
+g.close()
