@@ -93,7 +93,7 @@ struct dftgrid {
     std::vector<int> bf_center, bf_prim_off, center_exp_off, prim_exp, prim_lmn;
 
     // device: static tables
-    DevBuf<double> d_atom_xyz, d_Rdist, d_rtab, d_wrad, d_leb, d_Y, d_Yt, d_pre, d_lu, d_xs;
+    DevBuf<double> d_atom_xyz, d_Rdist, d_rtab, d_wrad, d_leb, d_Y, d_Yt, d_pre, d_pre_scaled, d_lu, d_xs;
     DevBuf<int> d_perm, d_lo, d_hi;
     DevBuf<double> d_spA, d_spCp, d_spDen, d_spH, d_spRh;
     SplineDev spline{};
@@ -603,6 +603,13 @@ void do_build(dftgrid* h) {
     h->d_Y.upload(Y, st);
     h->d_Yt.upload(Yt, st);
     h->d_pre.upload(pre, st);
+    {
+        // prefactors times the scale of k_interp_bin's Legendre recurrence (kernels_hartree.cuh: legendre_scale)
+        std::vector<double> pre_s(pre.size());
+        for (int l = 0; l <= g.lmax; l++)
+            for (int m = 0; m <= g.lmax; m++) pre_s[(size_t)l * (g.lmax + 1) + m] = pre[(size_t)l * (g.lmax + 1) + m] * (m <= l ? legendre_scale(l, m) : 1.0);
+        h->d_pre_scaled.upload(pre_s, st);
+    }
     h->d_lu.upload(lu.lu, st);
     h->d_perm.upload(lu.perm, st);
     h->d_lo.upload(lu.lo, st);
@@ -856,7 +863,8 @@ void run_potential(dftgrid* h) {
     const bool smp = sm_poisson <= 48 * 1024, sms = sm_spline <= 48 * 1024;
     k_poisson<<<(unsigned)((nsys + 63) / 64), 64, smp ? sm_poisson : 0, st>>>(g, g.nrad + 2, h->d_lu.p, h->d_perm.p, h->d_lo.p, h->d_hi.p,
                                                                               h->d_rtab.p, rho_lm, h->d_qatom.p, h->d_work.p, h->d_U_lm.p, smp);
-    k_spline<<<(unsigned)((nsys + 63) / 64), 64, sms ? sm_spline : 0, st>>>(g, h->spline, h->d_U_lm.p, h->d_pre.p, h->d_work.p, h->d_coef.p, sms);
+    k_spline<<<(unsigned)((nsys + 63) / 64), 64, sms ? sm_spline : 0, st>>>(g, h->spline, h->d_U_lm.p, h->binned ? h->d_pre_scaled.p : h->d_pre.p,
+                                                                            h->d_work.p, h->d_coef.p, sms);
     h->launches += 2;
     if (g.nloc > 0) {
         k_v_own<<<(unsigned)g.nshell_loc, 128, g.nlm * sizeof(double), st>>>(g, h->d_rtab.p, h->d_leb.p, h->d_Yt.p, h->d_U_lm.p, h->d_Vown.p);

@@ -617,6 +617,14 @@ __global__ void k_item_keys(const int* __restrict__ binoff, int nkeys, int unit,
     item_key[item] = key;
 }
 
+// Scale of the Legendre recurrence used by k_interp_bin (see there): K_l^m, and the one remaining constant A'_l^m.
+__host__ __device__ constexpr double legendre_scale(int l, int m) {
+    return l <= m + 1 ? 1.0 : (double)(l + m - 1) / (double)(l - m) * legendre_scale(l - 2, m);
+}
+__host__ __device__ constexpr double legendre_scaled_a(int l, int m) {
+    return (double)(2 * l - 1) / (double)(l - m) * legendre_scale(l - 1, m) / legendre_scale(l, m);
+}
+
 template <int I, int N, class F>
 __device__ __forceinline__ void static_for(F&& f) {
     if constexpr (I < N) {
@@ -693,10 +701,15 @@ k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __r
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncwarp();
-    // compile-time (m, l) loops: every recurrence constant and record offset is an immediate
+    // compile-time (m, l) loops: every recurrence constant and record offset is an immediate.  The Legendre column is run
+    // in the scaled form s_l = P_l^m / K_l^m with K chosen so that the three-term recurrence loses its second constant,
+    //   (l-m) P_l = (2l-1) x P_{l-1} - (l+m-1) P_{l-2}   ->   s_l = A'_l x s_{l-1} - s_{l-2},
+    //   K_m = K_{m+1} = 1,  K_l = (l+m-1)/(l-m) K_{l-2},  A'_l = (2l-1)/(l-m) K_{l-1}/K_l     (legendre_scale below),
+    // two FP64 operations per (l, m) instead of three; K_l^m is folded into the spline records by k_spline (scaled
+    // prefactor table), like the Y_lm prefactor.  The cos / sin(m phi) factors are applied once per m to the two l-sums.
     static_for<0, L + 1>([&](auto mc) {
         constexpr int m = decltype(mc)::value;
-        double pl1[R], pl2[R];
+        double pl1[R], pl2[R], accc[R], accs[R];
 #pragma unroll
         for (int j = 0; j < R; j++) {
             if (m > 0) {
@@ -707,6 +720,8 @@ k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __r
             }
             pl2[j] = 0.0;
             pl1[j] = pmm[j];
+            accc[j] = 0.0;
+            accs[j] = 0.0;
         }
         static_for<m, L + 1>([&](auto lc) {
             constexpr int l = decltype(lc)::value;
@@ -720,22 +735,27 @@ k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __r
                     pl = pmm[j];
                 } else if (l == m + 1) {
                     pl = ct[j] * (double)(2 * m + 1) * pmm[j];
-                } else {  // (l-m) P_l^m = (2l-1) x P_{l-1}^m - (l+m-1) P_{l-2}^m with the constants folded
-                    constexpr double A = (double)(2 * l - 1) / (double)(l - m > 0 ? l - m : 1);
-                    constexpr double B = (double)(-l - m + 1) / (double)(l - m > 0 ? l - m : 1);
-                    pl = fma(A, ct[j] * pl1[j], B * pl2[j]);
+                } else {
+                    constexpr double AP = legendre_scaled_a(l, m);
+                    pl = fma(AP * ct[j], pl1[j], -pl2[j]);
                 }
                 pl2[j] = pl1[j];
                 pl1[j] = pl;
                 const double svc = fma(fma(fma(cc.w, tt[j], cc.z), tt[j], cc.y), tt[j], cc.x);
+                accc[j] = fma(pl, svc, accc[j]);
                 if (m > 0) {
                     const double svs = fma(fma(fma(cs.w, tt[j], cs.z), tt[j], cs.y), tt[j], cs.x);
-                    acc[j] = fma(pl, fma(svs, sn[j], svc * cm[j]), acc[j]);
-                } else {
-                    acc[j] = fma(pl, svc, acc[j]);
+                    accs[j] = fma(pl, svs, accs[j]);
                 }
             }
         });
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if (m > 0)
+                acc[j] += fma(accs[j], sn[j], accc[j] * cm[j]);
+            else
+                acc[j] += accc[j];
+        }
     });
 #pragma unroll
     for (int j = 0; j < R; j++)

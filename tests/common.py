@@ -18,7 +18,30 @@ BECKE_FLOOR = 1e-3
 
 
 def load_golden(name):
-    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    """Fixture as a dict.  The large-configuration fixtures (make_golden_large.py) store symmetric matrices as packed upper
+    triangles (`X_triu`) and regenerate the synthetic P from its seed: both are expanded here (`X`, `P`)."""
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    nb = len(g["bf_nprim"])
+    for k in [k for k in g if k.endswith("_triu")]:
+        M = np.zeros((nb, nb))
+        M[np.triu_indices(nb)] = g[k]
+        g[k[:-5]] = M + np.triu(M, 1).T
+    if "P" not in g and "P_checksum" in g:
+        from dftcxx_b200.systems import synthetic_density
+
+        class _M:
+            nbf = nb
+            nelec = int(round(float(g["nel"])))
+
+        P = synthetic_density(_M)
+        chk = np.array([P.sum(), np.abs(P).sum(), np.trace(P)])
+        assert np.allclose(chk, g["P_checksum"], rtol=1e-13, atol=0), "synthetic P does not reproduce the fixture's"
+        g["P"] = P
+    return g
+
+
+def have_golden(name):
+    return os.path.exists(os.path.join(GOLDEN, name + ".npz"))
 
 
 def system_from_golden(g):

@@ -82,6 +82,32 @@ def test_scf_on_two_gpus_from_one_process(name):
         assert abs(float(et) - rr[0]) < 1.5e-7
 
 
+@pytest.mark.parametrize("name", ["h2o32_p631_fine", "c40h82_p631_fine"])
+def test_large_scf_trace_matches_reference_iteration_by_iteration(name):
+    """BASELINE configs 4 and 5 (i): the drop-in host (own integrals, own orthogonalisation, device-resident algebra) against
+    the unmodified reference's SCF iterations — total energy within 1e-8 Ha at equal iteration index.  (The reference's 50 %
+    mixing does not converge (H2O)32: its energies go -2195.55 -> -2211.83 -> ...; the point is to match it, not to fix it.)"""
+    from common import have_golden
+
+    if not have_golden(name):
+        pytest.skip("fixture not generated yet")
+    L, dp = hostlib()
+    g = load_golden(name)
+    ref = g["scf_energies"]
+    nit = len(ref)
+    for mode in (0, 1):
+        e = np.zeros((nit, 6))
+        enuc = ctypes.c_double()
+        n = L.dfthost_scf2(os.path.join(M.DATA, "molecules", name + ".in").encode(), 0, 1, mode, nit, nit, e.ctypes.data_as(dp),
+                           ctypes.cast(ctypes.byref(enuc), dp), None)
+        assert n == nit, L.dfthost_last_error()
+        assert abs(enuc.value - float(g["scf_enuc"])) < 1e-9
+        print(name, "mode", mode, "dE", np.abs(e[:, 0] - ref[:, 0]))
+        assert np.max(np.abs(e[:, 0] - ref[:, 0])) <= TOL_ENERGY, np.abs(e[:, 0] - ref[:, 0])
+        assert np.max(np.abs(e[:, 1] - ref[:, 1])) <= TOL_ENERGY and np.max(np.abs(e[:, 3] - ref[:, 3])) <= TOL_ENERGY
+        assert np.max(np.abs(e[:, 4] - ref[:, 4])) <= 1e-8
+
+
 def test_scf_stopping_rule_and_iteration_count():
     """Free-running SCF: the reference stops h2o/sto3g after 14 iterations at -72.9906070."""
     L, dp = hostlib()
