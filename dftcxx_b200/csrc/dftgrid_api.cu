@@ -331,11 +331,11 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSc
         // diagonal tile issues 17 of 32 DMMAs per warp (11.5), the 64-wide diagonal tile 8 of 32 (6.5; under-estimating
         // it makes its CTA the straggler, 5 costs 14 %)
         // a 32-wide edge tile (nb = 524 -> nbp = 544) issues a quarter of the DMMAs for the same A loads (6.5); its
-        // diagonal tile keeps four warps busy with 4 DMMAs per k4-step (3)
+        // diagonal tile keeps only four warps busy with 4 dependent DMMAs per k4-step (5; sweeps at C40H82: 3 costs 35 %)
         const int wj = std::min(kTileN, nbp - tj * kTileN);
         const bool narrow = wj <= 64, narrow32 = wj <= 32;
         const double c_narrow = nc ? std::atof(nc) : 10.5, c_diag = dc ? std::atof(dc) : 11.5, c_edge_diag = ec ? std::atof(ec) : 6.5;
-        const double c_n32 = n32c ? std::atof(n32c) : 6.5, c_d32 = d32c ? std::atof(d32c) : 3.0;
+        const double c_n32 = n32c ? std::atof(n32c) : 6.5, c_d32 = d32c ? std::atof(d32c) : 5.0;
         cost[it] = ti == tj ? (narrow32 ? c_d32 : narrow ? c_edge_diag : c_diag) : (narrow32 ? c_n32 : narrow ? c_narrow : 20.0);
         if (item_frac) cost[it] *= std::max(0.02, (*item_frac)[it % npairs]);  // never zero: every item keeps a segment
         W1 += cost[it];

@@ -464,7 +464,7 @@ __device__ __forceinline__ int con_count_owned(const ConSeg& sg, int x0, int x1,
     return cnt;
 }
 
-constexpr int kConTmaThreads = kDenseThreads + 32;
+constexpr int kConTmaThreads = kDenseThreads + 128;  // 2 DMMA warpgroups + 1 producer warpgroup: warp 8 operand A, warp 9 operand B and the weights
 constexpr size_t kConTmaSmemBytes = (size_t)kStages * kConStageDoubles * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
 
 // The chunk loop of one segment for one DMMA warp; `op` consumes one staged chunk.
@@ -696,7 +696,7 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) {
-            mbar_init(full + s, 1);   // the producer's arrive.expect_tx
+            mbar_init(full + s, 2);   // one arrive.expect_tx per producer warp
             mbar_init(empty + s, 8);  // one arrival per DMMA warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -705,8 +705,15 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
     const int s_begin = cta_seg_off[blockIdx.x], s_end = cta_seg_off[blockIdx.x + 1];
     const int nblock = bc > 0 ? (nchunk + bc - 1) / bc : 0;
     unsigned n = 0;  // running stage counter, continues across segments and blocks
-    if (warp == 8) {
-        // ===== producer warp: one 1 KB Phi row (per operand) per lane and stage; block-major, like the consumers =====
+    if (warp >= 8) {
+        // ===== producer warps: one Phi row per lane and stage; block-major, like the consumers.  Warp 8 copies the A
+        // operand (tile i's columns), warp 9 the B operand (tile j's, absent on the diagonal) and the weights: a bulk copy
+        // costs its issuing warp ~50 clocks, and with one warp issuing all 65 the narrow edge tiles (32 or 64 columns,
+        // a quarter or half of the DMMA work for the same number of copies) were producer-bound =====
+        // 384 threads start with 168 registers each; this warpgroup hands registers back, the DMMA warpgroups grow (as in k_rho_tma)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+        if (warp > 9) return;
+        const bool prodA = warp == 8;
         for (int b = 0; b < nblock; b++) {
             for (int sidx = s_begin; sidx < s_end; sidx++) {
                 const ConSeg sg = segs[sidx];
@@ -715,7 +722,7 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
                 const bool diag = ti == tj;
                 const double* d = sg.z == 0 ? d0 : d1;
                 const unsigned wi = (unsigned)min(kTileM, nbp - ci) * 8u, wj = (unsigned)min(kTileN, nbp - cj) * 8u;  // valid row bytes
-                const unsigned bytes = kTileK * (wi + (diag ? 0u : wj)) + kTileK * 8u;
+                const unsigned bytes = prodA ? kTileK * wi : kTileK * (diag ? 0u : wj) + kTileK * 8u;
                 const int x0 = min(b * bc, nchunk), x1 = min((b + 1) * bc, nchunk);
                 for (int base = x0; base < x1; base += 32) {
                     const int x = base + lane;
@@ -732,9 +739,12 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
                         if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes);
                         __syncwarp();
                         const double* row = phi + (row0 + lane) * (size_t)nbp;
-                        bulk_copy_g2s(st + lane * kLdN, row + ci, wi, full + stage);
-                        if (!diag) bulk_copy_g2s(st + kTileK * kLdN + lane * kLdN, row + cj, wj, full + stage);
-                        if (lane == 0) bulk_copy_g2s(st + 2 * kTileK * kLdN, d + row0, kTileK * 8u, full + stage);
+                        if (prodA) {
+                            bulk_copy_g2s(st + lane * kLdN, row + ci, wi, full + stage);
+                        } else {
+                            if (!diag) bulk_copy_g2s(st + kTileK * kLdN + lane * kLdN, row + cj, wj, full + stage);
+                            if (lane == 0) bulk_copy_g2s(st + 2 * kTileK * kLdN, d + row0, kTileK * 8u, full + stage);
+                        }
                         n++;
                     }
                 }
@@ -743,6 +753,7 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
         return;
     }
     // ===== DMMA warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
     // A CTA with a single segment keeps its accumulators in registers while the blocks go by.  A CTA whose share crosses
     // an item boundary (2-3 segments) visits its segments in turn inside every block and parks the accumulators of the
     // inactive ones in their partial tiles (L2-resident) in between.

@@ -325,7 +325,7 @@ def test_contraction_schedule_tiles_every_item_exactly_once(nbp, nchunk, nsm, nz
                 k -= nt - a
             wj = min(128, nbp - j * 128)
             if wj <= 32:
-                return 3.0 if i == j else 6.5
+                return 5.0 if i == j else 6.5
             return (6.5 if wj <= 64 else 11.5) if i == j else (10.5 if wj <= 64 else 20.0)
         share = [sum(cost(int(pair[s])) * (te[s] - tb[s]) / float(1 << 31) for s in range(cta_off[c], cta_off[c + 1])) for c in range(nctas.value)]
         assert max(share) - min(share) <= 1e-6 * max(share)
