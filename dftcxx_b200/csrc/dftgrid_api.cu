@@ -110,6 +110,9 @@ struct dftgrid {
     DevBuf<double> d_P, d_Praw, d_shell_raw, d_shell2, d_qatom, d_qatom2, d_scalars, d_rho_lm, d_U_lm, d_work, d_coef, d_partial, d_res;
     DevBuf<int> d_pairs, d_chunk_ids;
     DevBuf<unsigned long long> d_chunk_mask;  // screening map of the active chunks (k_chunk_masks), aligned with d_chunk_ids
+    DevBuf<unsigned long long> d_dbg_times;   // DFTGRID_DEBUG_CTA_TIMES
+    DevBuf<int> d_con_chunk_ids;              // the active chunks in the contraction's shuffled sweep order, and their maps
+    DevBuf<unsigned long long> d_con_chunk_mask;
     bool screened = false;
     double screen_work_fraction = 1.0;
     // stream-K schedules of the contraction: [0] two matrices (XC, J), [1] one matrix (fused Fock build)
@@ -459,21 +462,53 @@ void build_active_lists(dftgrid* h, int nsm) {
     h->screened = screen;
     if (screen) h->d_chunk_mask.upload(act_masks, st);
     CK(cudaStreamSynchronize(st));
-    // work fraction of every tile pair under the map: a stage costs the pair as much as its busiest warp, i.e. (any
-    // significant block of tile i) x (fraction of tile j's blocks that are significant); skipped chunks cost nothing
+    // The contraction sweeps the active chunks in a golden-ratio shuffled order when the map is in use: any window of
+    // positions then holds chunks of all atoms and radii, every tile pair pays its AVERAGE cost per window, and the CTAs
+    // (whose shares are equalised on those averages) keep passing over the Phi rows in step, which is what lets a row's
+    // ~14 uses hit the L2.  (In atom-major order a pair is cheap far from its atoms and expensive near them; the CTAs
+    // drift apart by thousands of chunks and DRAM reads triple: measured 6.5 -> 18 GB.)
     std::vector<double> item_frac;
     if (screen && h->n_active_chunks > 0) {
+        const long n = h->n_active_chunks;
+        std::vector<std::pair<double, int>> key((size_t)n);
+        for (long k = 0; k < n; k++) {
+            const double f = (double)k * 0.6180339887498949;
+            key[k] = {f - std::floor(f), (int)k};
+        }
+        std::sort(key.begin(), key.end());
+        std::vector<int> con_ids((size_t)n);
+        std::vector<unsigned long long> con_masks((size_t)n);
+        for (long t = 0; t < n; t++) {
+            con_ids[t] = chunk_ids[key[t].second];
+            con_masks[t] = act_masks[key[t].second];
+        }
+        h->d_con_chunk_ids.upload(con_ids, st);
+        h->d_con_chunk_mask.upload(con_masks, st);
+        CK(cudaStreamSynchronize(st));
+        // work fraction of every tile pair under the map: a stage costs the pair as much as its busiest DMMA warp
+        // (kernels_dense.cuh ConMode*::mma), a chunk with an insignificant tile is not staged at all
+        // A staged chunk never costs less than the pipeline's own turnaround (the producers' ~33 bulk copies each, the
+        // barrier round trip): a floor on the per-stage fraction, calibrated by sweeps (DFTGRID_STAGE_FLOOR).
+        double floor_ = 0.25;
+        if (const char* e = std::getenv("DFTGRID_STAGE_FLOOR")) floor_ = std::atof(e);
         const int nt = (h->nbp + kTileM - 1) / kTileM;
         for (int ti = 0; ti < nt; ti++)
             for (int tj = ti; tj < nt; tj++) {
                 const int nbj = std::min(4, nblk - 4 * tj);
-                const unsigned long long mi = 0xFull << (4 * ti), mj = (nbj >= 4 ? 0xFull : ((1ull << nbj) - 1ull)) << (4 * tj);
                 double acc = 0.0;
-                for (long x = 0; x < h->n_active_chunks; x++) {
+                for (long x = 0; x < n; x++) {
                     const unsigned long long cm = act_masks[x];
-                    if ((cm & mi) && (cm & mj)) acc += (double)__builtin_popcountll(cm & mj) / nbj;
+                    const unsigned ab = (unsigned)(cm >> (4 * ti)) & 0xFu, bb = (unsigned)(cm >> (4 * tj)) & ((1u << nbj) - 1u);
+                    if (!ab || !bb) continue;
+                    if (ti != tj) {
+                        acc += std::max(floor_, (double)__builtin_popcount(bb) / nbj);
+                    } else if (nbj == 4) {  // triangular diagonal tile: staged chunks run the full stage
+                        acc += 1.0;
+                    } else {
+                        acc += std::max(floor_, (double)__builtin_popcount(bb) / nbj);
+                    }
                 }
-                item_frac.push_back(acc / (double)h->n_active_chunks);
+                item_frac.push_back(acc / (double)n);
             }
         double mean = 0.0;
         for (double f : item_frac) mean += f;
@@ -493,9 +528,11 @@ void build_active_lists(dftgrid* h, int nsm) {
             h->d_rho_part.zero(st);  // skipped (all-zero) chunks are never written
         }
     }
-    // (the contraction itself is not screened: per-chunk skipping breaks the lockstep sweep its L2 sharing rests on — measured:
-    // DRAM reads 6.5 -> 18 GB, 12.3 -> 17.1 ms — so its schedule keeps the plain per-item costs; the fraction is reported only)
-    build_contract_schedule(h, h->n_active_chunks, nsm, nullptr);
+    build_contract_schedule(h, h->n_active_chunks, nsm, item_frac.empty() ? nullptr : &item_frac);
+    if (std::getenv("DFTGRID_DEBUG_CTA_TIMES")) {
+        h->d_dbg_times.alloc(2 * (size_t)nsm + 2);
+        for (size_t i = 0; i < item_frac.size(); i++) std::fprintf(stderr, "[dftgrid] pair %zu work fraction %.3f\n", i, item_frac[i]);
+    }
 }
 
 // Sort the (local point, source atom) pairs of the cross-atom interpolation into (atom, spline interval) bins.
@@ -954,8 +991,19 @@ void run_contract(dftgrid* h, int mode) {
         h->peer_used = true;
         h->launches++;
     }
-    k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, fock ? h->d_dF.p : h->d_dxc.p, h->d_dJ.p, h->d_chunk_ids.p, h->d_pairs.p,
-                                                                     D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc);
+    k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, fock ? h->d_dF.p : h->d_dxc.p, h->d_dJ.p,
+                                                                     h->screened ? h->d_con_chunk_ids.p : h->d_chunk_ids.p,
+                                                                     h->screened ? h->d_con_chunk_mask.p : nullptr, h->d_pairs.p, D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc, h->d_dbg_times.p);
+    if (h->d_dbg_times.p && !h->capturing) {
+        // developer instrumentation: per-CTA wall time of the contraction with the CTA's segments
+        std::vector<unsigned long long> t(2 * (size_t)D.ctas);
+        CK(cudaMemcpyAsync(t.data(), h->d_dbg_times.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        unsigned long long t0 = ~0ull;
+        for (int c = 0; c < D.ctas; c++) t0 = std::min(t0, t[2 * c]);
+        std::fprintf(stderr, "[dftgrid] contraction CTA times (start us, duration us) mode %d\n", mode);
+        for (int c = 0; c < D.ctas; c++) std::fprintf(stderr, "  cta %3d  %8.1f %8.1f\n", c, (t[2 * c] - t0) * 1e-3, (t[2 * c + 1] - t[2 * c]) * 1e-3);
+    }
     double* res = fock ? h->d_fres.p : h->d_res.p;
     if (h->peer_ready) {
         // split-K reduction straight into this rank's exchange buffer, then the cross-rank sum over peer memory

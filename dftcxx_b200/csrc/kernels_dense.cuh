@@ -360,7 +360,8 @@ __global__ void k_rho_combine(const double* __restrict__ part, long part_stride,
 // =========================================================================================================
 // C_z = Phi^T diag(d_z) Phi  (upper-triangular 128x128 tile pairs, split over point ranges)
 // =========================================================================================================
-constexpr int kConStageDoubles = 2 * kTileK * kLdN + kTileK;
+constexpr int kConMaskOff = 2 * kTileK * kLdN + kTileK;  // 8-byte slot after the weights: the staged chunk's block map
+constexpr int kConStageDoubles = kConMaskOff + 2;         // (+2 keeps every stage 16-byte aligned for the bulk copies)
 
 // Warp tiling of the 128 x (128|64) output tile: 8 warps stacked along M, each owning MT = 2 row tiles (16 rows) and
 // the whole width (NT = 16 column tiles, 8 for an edge tile).  Per k4-step a warp then scales only 2 A fragments by the
@@ -386,6 +387,34 @@ __device__ __forceinline__ void con_mma_stage(const double* st, double (&acc)[32
     }
 }
 
+
+// The same when some of the tile's 32-column blocks are insignificant for this chunk (screening, k_chunk_masks): bbits bit
+// g = column tiles 4g .. 4g+3 are needed.  Warp-uniform branches around groups of static DMMAs.
+template <int MT, int NT>
+__device__ __forceinline__ void con_mma_stage_masked(const double* st, double (&acc)[32][2], int warp, int lane, unsigned bbits) {
+    const double* As = st;
+    const double* Bs = st + kTileK * kLdN;
+    const double* ds = st + 2 * kTileK * kLdN;
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < kTileK; kk += 4) {
+        double a[MT];
+        const double dv = ds[kk + q];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) a[mt] = As[(kk + q) * kLdN + warp * (MT * 8) + mt * 8 + g] * dv;
+#pragma unroll
+        for (int grp = 0; grp < NT / 4; grp++)
+            if ((bbits >> grp) & 1u) {
+                double b[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) b[t] = Bs[(kk + q) * kLdN + (grp * 4 + t) * 8 + g];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int t = 0; t < 4; t++) dmma884(acc[mt * NT + grp * 4 + t][0], acc[mt * NT + grp * 4 + t][1], a[mt], b[t]);
+            }
+    }
+}
 
 // Diagonal tile pair (ti == tj), full 128 wide: only the 8x8 DMMA tiles on or above the diagonal are needed.  Warp W
 // owns row tile W (against column tiles W..15) and row tile 15-W (against column tiles 15-W..15): 17 DMMAs per
@@ -414,6 +443,21 @@ __device__ __forceinline__ void con_mma_stage_tri(const double* st, double (&acc
     }
 }
 
+
+// 64-wide diagonal edge tile with only some column blocks significant (bits 0, 1)
+__device__ __forceinline__ void con_mma_stage_diag_edge_half(const double* st, double (&acc)[32][2], int warp, int lane, unsigned bits) {
+    const double* As = st;
+    const double* ds = st + 2 * kTileK * kLdN;
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < kTileK; kk += 4) {
+        const double dv = ds[kk + q];
+        const double a0 = As[(kk + q) * kLdN + warp * 8 + g] * dv;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+            if ((bits >> (nt >> 2)) & 1u) dmma884(acc[nt][0], acc[nt][1], a0, As[(kk + q) * kLdN + nt * 8 + g]);
+    }
+}
 
 // 64-wide diagonal edge tile: warp w owns row tile w against the 8 column tiles (the tile is 1 of ~28 pairs).
 __device__ __forceinline__ void con_mma_stage_diag_edge(const double* st, double (&acc)[32][2], int warp, int lane) {
@@ -449,17 +493,25 @@ struct ConSeg {
     unsigned tb, te;  // [tb, te) in units of 2^-31
 };
 
-__device__ __forceinline__ bool con_owns(const ConSeg& sg, int x) {
+// Screening (k_chunk_masks): a chunk whose amplitudes are insignificant in ALL of tile i's column blocks, or in all of
+// tile j's, contributes nothing to the pair and is not staged at all: ownership = hash range AND both tiles significant.
+// mi / mj: the tiles' block bits inside a chunk map; cm: the chunk's map (all ones without a map).  The chunk positions x
+// are an interleaved order of the active chunks (dftgrid_api.cu), so that any window of positions mixes chunks of all atoms
+// and every tile pair pays its average cost per window: the CTAs keep sweeping the Phi rows in step (L2 sharing).
+__device__ __forceinline__ bool con_owns(const ConSeg& sg, int x, unsigned long long cm, unsigned long long mi, unsigned long long mj) {
     const unsigned u = ((unsigned)x * 2654435769u) >> 1;
-    return u >= sg.tb && u < sg.te;
+    return u >= sg.tb && u < sg.te && (cm & mi) != 0ull && (cm & mj) != 0ull;
 }
+__device__ __forceinline__ unsigned long long con_tile_bits(int t) { return 0xFull << (4 * t); }
 
 // Number of chunk positions of [x0, x1) owned by the segment (warp-collective, same value in every lane).
-__device__ __forceinline__ int con_count_owned(const ConSeg& sg, int x0, int x1, int lane) {
+__device__ __forceinline__ int con_count_owned(const ConSeg& sg, int x0, int x1, int lane, const unsigned long long* __restrict__ chunk_mask,
+                                               unsigned long long mi, unsigned long long mj) {
     int cnt = 0;
     for (int base = x0; base < x1; base += 32) {
         const int x = base + lane;
-        cnt += __popc(__ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x)));
+        const unsigned long long cm = (x < x1 && chunk_mask) ? chunk_mask[x] : ~0ull;
+        cnt += __popc(__ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x, cm, mi, mj)));
     }
     return cnt;
 }
@@ -483,8 +535,16 @@ __device__ __forceinline__ void con_run_segment(const double* sm, unsigned long 
 
 // Accumulator tile layouts of the four segment kinds: how the DMMA stage, the store to and the reload from the
 // segment's partial tile address the 32 accumulator pairs.
+// abits / bbits: significance of the four 32-column blocks of tile i (the A rows; warp w's rows lie in block w / 2) and of
+// tile j for the staged chunk.
 struct ConModeFull {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 16>(st, acc, warp, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned bbits) {
+        if (!((abits >> (warp >> 1)) & 1u)) return;
+        if (bbits == 0xFu)
+            con_mma_stage<2, 16>(st, acc, warp, lane);
+        else
+            con_mma_stage_masked<2, 16>(st, acc, warp, lane, bbits);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -504,7 +564,13 @@ struct ConModeFull {
     }
 };
 struct ConModeNarrow {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 8>(st, acc, warp, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned bbits) {
+        if (!((abits >> (warp >> 1)) & 1u)) return;
+        if ((bbits & 3u) == 3u)
+            con_mma_stage<2, 8>(st, acc, warp, lane);
+        else
+            con_mma_stage_masked<2, 8>(st, acc, warp, lane, bbits);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -525,7 +591,10 @@ struct ConModeNarrow {
 };
 // 32-wide edge tile (nbp = 128 k + 32, e.g. nb = 524): 4 column tiles instead of 8
 struct ConModeNarrow32 {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage<2, 4>(st, acc, warp, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned bbits) {
+        if (!((abits >> (warp >> 1)) & 1u) || !(bbits & 1u)) return;
+        con_mma_stage<2, 4>(st, acc, warp, lane);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -546,8 +615,8 @@ struct ConModeNarrow32 {
 };
 // 32-wide diagonal edge tile: warps 0-3 own row tile w against the 4 column tiles, warps 4-7 only follow the pipeline
 struct ConModeDiagEdge32 {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) {
-        if (warp >= 4) return;
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned) {
+        if (warp >= 4 || !(abits & 1u)) return;
         const double* As = st;
         const double* ds = st + 2 * kTileK * kLdN;
         const int g = lane >> 2, q = lane & 3;
@@ -580,7 +649,13 @@ struct ConModeDiagEdge32 {
     }
 };
 struct ConModeDiagEdge {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane) { con_mma_stage_diag_edge(st, acc, warp, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int warp, int lane, unsigned abits, unsigned) {
+        if (!((abits >> (warp >> 2)) & 1u)) return;  // row tile w lies in block w / 4
+        if ((abits & 3u) == 3u)
+            con_mma_stage_diag_edge(st, acc, warp, lane);
+        else
+            con_mma_stage_diag_edge_half(st, acc, warp, lane, abits);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int warp, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -599,7 +674,13 @@ struct ConModeDiagEdge {
 };
 template <int W>
 struct ConModeTri {
-    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int, int lane) { con_mma_stage_tri<W>(st, acc, lane); }
+    static __device__ __forceinline__ void mma(const double* st, double (&acc)[32][2], int, int lane, unsigned abits, unsigned) {
+        // a staged diagonal chunk always runs the full triangular stage: the per-tile predicates of a masked variant
+        // (17 differently conditioned DMMAs per k4-step) cost more than the skipped DMMAs save (measured: the diagonal
+        // items became 2x stragglers); diagonal tiles still skip the chunks in which the whole tile is insignificant
+        (void)abits;
+        con_mma_stage_tri<W>(st, acc, lane);
+    }
     template <bool LOAD>
     static __device__ __forceinline__ void io(double* out, double (&acc)[32][2], int, int lane) {
         const int g = lane >> 2, q = lane & 3;
@@ -634,7 +715,7 @@ struct ConModeTri {
 template <class Mode>
 __device__ __forceinline__ void con_segment_blocks_mode(const double* sm, unsigned long long* full, unsigned long long* empty, unsigned& n, int warp,
                                                         int lane, const ConSeg& sg, double* out, int nchunk, int bc, int b_begin, int b_end,
-                                                        bool fresh) {
+                                                        bool fresh, const unsigned long long* __restrict__ chunk_mask, int ti, int tj) {
     double acc[32][2];
     if (fresh) {
 #pragma unroll
@@ -644,19 +725,23 @@ __device__ __forceinline__ void con_segment_blocks_mode(const double* sm, unsign
     }
     {
         const int x0 = min(b_begin * bc, nchunk), x1 = min(b_end * bc, nchunk);
-        con_run_segment(sm, full, empty, con_count_owned(sg, x0, x1, lane), n, lane, [&](const double* st) { Mode::mma(st, acc, warp, lane); });
+        con_run_segment(sm, full, empty, con_count_owned(sg, x0, x1, lane, chunk_mask, con_tile_bits(ti), con_tile_bits(tj)), n, lane,
+                        [&](const double* st) {
+                            const unsigned long long cm = *reinterpret_cast<const unsigned long long*>(st + kConMaskOff);
+                            Mode::mma(st, acc, warp, lane, (unsigned)(cm >> (4 * ti)) & 0xFu, (unsigned)(cm >> (4 * tj)) & 0xFu);
+                        });
     }
     Mode::template io<false>(out, acc, warp, lane);
 }
 
 __device__ __forceinline__ void con_segment_blocks(const double* sm, unsigned long long* full, unsigned long long* empty, unsigned& n, int warp, int lane,
                                                    const ConSeg sg, const int* __restrict__ pair_ij, double* out, int nbp, int nchunk, int bc,
-                                                   int b_begin, int b_end, bool fresh) {
+                                                   int b_begin, int b_end, bool fresh, const unsigned long long* __restrict__ chunk_mask) {
     const int ti = pair_ij[2 * sg.pair], tj = pair_ij[2 * sg.pair + 1];
     const bool diag = ti == tj;
     const int wj = min(kTileN, nbp - tj * kTileN);
     const bool narrow = wj <= 64, narrow32 = wj <= 32;
-#define DFG_SEG_ARGS sm, full, empty, n, warp, lane, sg, out, nchunk, bc, b_begin, b_end, fresh
+#define DFG_SEG_ARGS sm, full, empty, n, warp, lane, sg, out, nchunk, bc, b_begin, b_end, fresh, chunk_mask, ti, tj
     if (!diag) {
         if (narrow32)
             con_segment_blocks_mode<ConModeNarrow32>(DFG_SEG_ARGS);
@@ -688,8 +773,9 @@ __device__ __forceinline__ void con_segment_blocks(const double* sm, unsigned lo
 // nchunk = number of non-zero chunks (length of chunk_ids), bc = chunks per L2 block.
 __global__ void __launch_bounds__(kConTmaThreads, 1)
 k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, const double* __restrict__ d1, const int* __restrict__ chunk_ids,
-               const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs, const int* __restrict__ cta_seg_off,
-               double* __restrict__ partial, int nbp, int nchunk, int bc) {
+               const unsigned long long* __restrict__ chunk_mask, const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs,
+               const int* __restrict__ cta_seg_off, double* __restrict__ partial, int nbp, int nchunk, int bc,
+               unsigned long long* __restrict__ dbg_times = nullptr) {
     extern __shared__ __align__(128) double sm[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)kStages * kConStageDoubles);
     unsigned long long* empty = full + kStages;
@@ -724,19 +810,26 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
                 const unsigned wi = (unsigned)min(kTileM, nbp - ci) * 8u, wj = (unsigned)min(kTileN, nbp - cj) * 8u;  // valid row bytes
                 const unsigned bytes = prodA ? kTileK * wi : kTileK * (diag ? 0u : wj) + kTileK * 8u;
                 const int x0 = min(b * bc, nchunk), x1 = min((b + 1) * bc, nchunk);
+                const unsigned long long mi = con_tile_bits(ti), mj = con_tile_bits(tj);
                 for (int base = x0; base < x1; base += 32) {
                     const int x = base + lane;
-                    unsigned mask = __ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x));
+                    const unsigned long long cm = (x < x1 && chunk_mask) ? chunk_mask[x] : ~0ull;
+                    unsigned mask = __ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x, cm, mi, mj));
                     const int my_chunk = x < x1 ? chunk_ids[x] : 0;
                     while (mask) {
                         const int src = __ffs(mask) - 1;
                         mask &= mask - 1u;
                         const size_t row0 = (size_t)__shfl_sync(0xffffffffu, my_chunk, src) * kTileK;
+                        const unsigned long long cmx = __shfl_sync(0xffffffffu, cm, src);
                         const unsigned stage = n % kStages, round = n / kStages;
                         double* st = sm + (size_t)stage * kConStageDoubles;
                         stress_delay(1, n);
                         mbar_wait(empty + stage, (round & 1u) ^ 1u);
-                        if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes);
+                        if (lane == 0) {
+                            // the chunk's block map travels with the stage (plain store, released by the arrive below)
+                            if (prodA) *reinterpret_cast<unsigned long long*>(st + kConMaskOff) = cmx;
+                            mbar_arrive_expect_tx(full + stage, bytes);
+                        }
                         __syncwarp();
                         const double* row = phi + (row0 + lane) * (size_t)nbp;
                         if (prodA) {
@@ -754,22 +847,30 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
     }
     // ===== DMMA warps =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
+    unsigned long long dbg_t0 = 0;
+    if (dbg_times && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(dbg_t0));
     // A CTA with a single segment keeps its accumulators in registers while the blocks go by.  A CTA whose share crosses
     // an item boundary (2-3 segments) visits its segments in turn inside every block and parks the accumulators of the
     // inactive ones in their partial tiles (L2-resident) in between.
     const int nseg = s_end - s_begin;
     if (nseg == 1) {
         con_segment_blocks(sm, full, empty, n, warp, lane, segs[s_begin], pair_ij, partial + (size_t)s_begin * (size_t)(kTileM * kTileN), nbp, nchunk, bc,
-                           0, nblock, true);
+                           0, nblock, true, chunk_mask);
     } else {
         for (int b = 0; b < nblock; b++)
             for (int sidx = s_begin; sidx < s_end; sidx++)
                 con_segment_blocks(sm, full, empty, n, warp, lane, segs[sidx], pair_ij, partial + (size_t)sidx * (size_t)(kTileM * kTileN), nbp, nchunk,
-                                   bc, b, b + 1, b == 0);
+                                   bc, b, b + 1, b == 0, chunk_mask);
         if (nblock == 0)  // empty shard: the reduction still reads every segment's tile
             for (int sidx = s_begin; sidx < s_end; sidx++)
                 con_segment_blocks(sm, full, empty, n, warp, lane, segs[sidx], pair_ij, partial + (size_t)sidx * (size_t)(kTileM * kTileN), nbp, nchunk,
-                                   bc, 0, 0, true);
+                                   bc, 0, 0, true, chunk_mask);
+    }
+    if (dbg_times && tid == 0) {  // developer instrumentation (DFTGRID_DEBUG_CTA_TIMES): wall time of this CTA's DMMA warps
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+        dbg_times[2 * blockIdx.x] = dbg_t0;
+        dbg_times[2 * blockIdx.x + 1] = t1;
     }
 }
 

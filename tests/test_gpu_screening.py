@@ -47,7 +47,9 @@ def test_screening_thresholds(name):
     exact = run(name, 0.0)
     dflt = run(name, None)
     loose = run(name, 1e-6)
-    assert off["frac"] == 1.0 and exact["frac"] <= 1.0 and dflt["frac"] <= exact["frac"] and loose["frac"] < dflt["frac"]
+    # (the reported fraction is the contraction's; a basis of one 128-tile has only a diagonal tile, which is never masked)
+    assert off["frac"] == 1.0 and exact["frac"] <= 1.0 and dflt["frac"] <= exact["frac"] and loose["frac"] <= dflt["frac"]
+    assert name == "h2o8" or loose["frac"] < dflt["frac"]
     # exact zeros only: the density kernel has no cross-CTA split, so rho is bit-identical; the contraction's stream-K
     # shares move with the map, so J / XC / F agree to summation-order rounding
     assert np.array_equal(exact["rho"], off["rho"]) and exact["nel"] == off["nel"]
