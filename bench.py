@@ -427,7 +427,7 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # ---- roofline of the dominant kernel (the DMMA contraction of F_grid), live event timings of the last fused step
-    npts_loc = g.npoints / ngpus_total if single_process else g.nloc
+    npts_loc = g.npoints / ngpus_total  # the mean shard (shards are cut at equal estimated work, not equal point counts)
     flops_contract = 1.0 * npts_loc * mol.nbf * (mol.nbf + 1)  # one symmetric matrix: Npts*nb*(nb+1) flop
     con_ms = max_over_ranks(phases["contract"])
     rho_ms = max_over_ranks(phases["rho"])

@@ -591,6 +591,67 @@ void build_pair_bins(dftgrid* h) {
     h->binned = true;
 }
 
+// This rank's contiguous block of the (atom, radial shell) units.  With screening the tensor work of a shell depends on
+// how many 32-column blocks of Phi are significant on it (a shell far from most atoms is cheap), so equal shell COUNTS
+// (dftgrid_shard_range) leave the ranks up to ~20 % out of balance; the blocks are therefore cut at equal estimated WORK:
+//   w(shell) = (significant blocks / blocks)^2 [rho and the contraction] + 0.25 [interpolation, pointwise work]
+// where a block counts as significant on shell (a, r) when some basis function f in it has | |R_a - R_f| - r | < reach_f,
+// reach_f = the distance beyond which |phi_f| <= tau by the bound sum_k |c_k N_k| d^L exp(-alpha_k d^2).  Pure host
+// arithmetic on replicated data: every rank computes the same cuts.  Single rank, or screening off: the plain rule.
+void shard_shells(dftgrid* h, const std::vector<double>& rtab, long nshell, long* first, long* count) {
+    double tau = 1e-20;
+    if (const char* e = std::getenv("DFTGRID_SCREEN_TAU")) tau = std::atof(e);
+    const int nblk = h->nbp / 32;
+    if (h->nranks == 1 || tau < 0.0 || nblk > 64 || std::getenv("DFTGRID_NO_ZERO_SKIP") || std::getenv("DFTGRID_EQUAL_SHARDS")) {
+        dftgrid_shard_range(nshell, h->rank, h->nranks, first, count);
+        return;
+    }
+    const double tau_eff = std::max(tau, 1e-300);
+    std::vector<double> reach(h->nbf, 0.0);
+    for (int f = 0; f < h->nbf; f++) {
+        double rf = 0.25;
+        for (double d = 0.25; d <= 80.0; d += 0.25) {
+            double b = 0.0;
+            for (int k = h->bf_prim_off[f]; k < h->bf_prim_off[f + 1]; k++) {
+                const int code = h->prim_lmn[k], L = (code & 15) + ((code >> 4) & 15) + ((code >> 8) & 15);
+                b += std::fabs(h->prim_coeff[k] * h->prim_norm[k]) * std::pow(d, L) * std::exp(-h->exp_alpha[h->prim_exp[k]] * d * d);
+            }
+            if (b > tau_eff) rf = d + 0.25;
+        }
+        reach[f] = rf;
+    }
+    const int nrad = h->prm.radial_points, na = h->natoms;
+    std::vector<double> cum((size_t)nshell + 1, 0.0);
+    std::vector<double> dist(h->nbf);
+    for (int a = 0; a < na; a++) {
+        for (int f = 0; f < h->nbf; f++) {
+            const double* c = &h->center_xyz[3 * (size_t)h->bf_center[f]];
+            const double dx = c[0] - h->atom_xyz[3 * a], dy = c[1] - h->atom_xyz[3 * a + 1], dz = c[2] - h->atom_xyz[3 * a + 2];
+            dist[f] = std::sqrt(dx * dx + dy * dy + dz * dz);
+        }
+        for (int i = 0; i < nrad; i++) {
+            int nsig = 0;
+            for (int b = 0; b < nblk; b++) {
+                bool sig = false;
+                for (int f = 32 * b; f < std::min(h->nbf, 32 * b + 32) && !sig; f++) sig = std::fabs(dist[f] - rtab[i]) < reach[f];
+                nsig += sig ? 1 : 0;
+            }
+            const double fsig = (double)nsig / nblk;
+            cum[(size_t)a * nrad + i + 1] = cum[(size_t)a * nrad + i] + fsig * fsig + 0.25;
+        }
+    }
+    const double total = cum[nshell];
+    auto cut = [&](int r) -> long {  // first shell whose cumulative work reaches r/nranks of the total
+        if (r <= 0) return 0;
+        if (r >= h->nranks) return nshell;
+        const double target = total * r / h->nranks;
+        return (long)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+    };
+    const long lo = cut(h->rank), hi = std::max(lo, cut(h->rank + 1));
+    *first = std::min(lo, nshell);
+    *count = std::min(hi, nshell) - *first;
+}
+
 void do_build(dftgrid* h) {
     const dftgrid_params& prm = h->prm;
     if (prm.lebedev_order < 0 || prm.lebedev_order > 10) throw std::runtime_error("lebedev_order must be 0..10");
@@ -604,13 +665,13 @@ void do_build(dftgrid* h) {
     g.nlm = (prm.lmax + 1) * (prm.lmax + 1);
     g.npts = (long)g.natoms * g.nrad * g.nang;
     const long nshell = (long)g.natoms * g.nrad;
-    dftgrid_shard_range(nshell, h->rank, h->nranks, &g.shell0, &g.nshell_loc);
-    g.nloc = g.nshell_loc * g.nang;
     h->leb_off = lebedev_offset(prm.lebedev_order);
 
     // ---- host tables
     std::vector<double> r, wr, Y, pre;
     make_radial(g.nrad, r, wr);
+    shard_shells(h, r, nshell, &g.shell0, &g.nshell_loc);
+    g.nloc = g.nshell_loc * g.nang;
     make_ylm_table(h->leb_off, g.nang, g.lmax, Y, pre);
     std::vector<double> Yt((size_t)g.nang * g.nlm);
     for (int j = 0; j < g.nang; j++)

@@ -79,7 +79,9 @@ int dftgrid_ngpus(const dftgrid_t* h);
 void dftgrid_destroy(dftgrid_t* h);
 
 /* The shard of rank `rank` out of `nranks`: a contiguous block of the natoms*nrad (atom, radial shell) units, balanced by
- * count.  Pure host arithmetic (no device needed); dftgrid_build uses exactly this rule. */
+ * count.  Pure host arithmetic (no device needed).  dftgrid_build uses this rule when the screening of Phi is off; with
+ * screening (the default) it cuts the same contiguous blocks at equal estimated WORK instead (a shell far from most atoms
+ * is cheap; see shard_shells in csrc/dftgrid_api.cu) — dftgrid_point_offset / dftgrid_npoints_local report the result. */
 int dftgrid_shard_range(long nshell_total, int rank, int nranks, long* first_shell, long* nshell);
 
 /* NCCL wiring for nranks > 1.  id is a 128-byte opaque blob produced on rank 0 and handed to every rank. */
