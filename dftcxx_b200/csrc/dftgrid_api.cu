@@ -71,6 +71,20 @@ struct DevBuf {
 
 }  // namespace
 
+namespace {
+// Stream-K schedule of the [XC | J] contraction (see kernels_dense.cuh): the items' costs for ONE chunk are laid end to
+// end and cut into equal shares, one per CTA (one CTA per SM); a share is 1-3 segments given as fixed-point fractions
+// of the item's chunks (which chunks those are is decided on the device by a low-discrepancy hash).
+struct ContractSchedule {
+    std::vector<int> pairs;     // [npairs][2] upper-triangular tile pairs
+    std::vector<ConSeg> segs;   // CTA after CTA; an item's segments are consecutive
+    std::vector<int> cta_off;   // [nctas+1] into segs
+    std::vector<int> item_off;  // [nitems+1] into segs, item = z * npairs + pair
+    int npairs = 0, bc = 1;
+};
+
+}  // namespace
+
 struct dftgrid_group;
 struct dftgrid {
     int device = 0, rank = 0, nranks = 1;
@@ -113,8 +127,9 @@ struct dftgrid {
     DevBuf<unsigned long long> d_dbg_times;   // DFTGRID_DEBUG_CTA_TIMES
     DevBuf<int> d_con_chunk_ids;              // the active chunks in the contraction's shuffled sweep order, and their maps
     DevBuf<unsigned long long> d_con_chunk_mask;
-    bool screened = false;
+    bool screened = false, calibrated = false;
     double screen_work_fraction = 1.0;
+    ContractSchedule host_sched;  // host copy of the fused schedule (calibration)
     // stream-K schedules of the contraction: [0] two matrices (XC, J), [1] one matrix (fused Fock build)
     struct DevSchedule {
         DevBuf<ConSeg> segs;
@@ -294,22 +309,12 @@ float elapsed(dftgrid* h, int a, int b) {
     return ms;
 }
 
-// Stream-K schedule of the [XC | J] contraction (see kernels_dense.cuh): the items' costs for ONE chunk are laid end to
-// end and cut into equal shares, one per CTA (one CTA per SM); a share is 1-3 segments given as fixed-point fractions
-// of the item's chunks (which chunks those are is decided on the device by a low-discrepancy hash).
-struct ContractSchedule {
-    std::vector<int> pairs;     // [npairs][2] upper-triangular tile pairs
-    std::vector<ConSeg> segs;   // CTA after CTA; an item's segments are consecutive
-    std::vector<int> cta_off;   // [nctas+1] into segs
-    std::vector<int> item_off;  // [nitems+1] into segs, item = z * npairs + pair
-    int npairs = 0, bc = 1;
-};
-
 // Pure host arithmetic (no device): also exported as dftgrid_debug_contract_schedule for the CPU test-suite.
 // item_frac (optional, [npairs]): mean fraction of a full stage's DMMA work that a chunk costs the tile pair under the
 // screening map (1 = every block of every chunk significant); the items' costs are scaled by it so that the CTAs' shares
 // stay equal in time.
-void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSchedule& S, const std::vector<double>* item_frac = nullptr) {
+void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSchedule& S, const std::vector<double>* item_frac = nullptr,
+                               const std::vector<double>* pair_cost = nullptr) {
     S = ContractSchedule();
     const int nt = (nbp + kTileM - 1) / kTileM;
     for (int i = 0; i < nt; i++)
@@ -341,6 +346,7 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSc
         const double c_n32 = n32c ? std::atof(n32c) : 6.5, c_d32 = d32c ? std::atof(d32c) : 5.0;
         cost[it] = ti == tj ? (narrow32 ? c_d32 : narrow ? c_edge_diag : c_diag) : (narrow32 ? c_n32 : narrow ? c_narrow : 20.0);
         if (item_frac) cost[it] *= std::max(0.02, (*item_frac)[it % npairs]);  // never zero: every item keeps a segment
+        if (pair_cost) cost[it] = std::max(1e-3, (*pair_cost)[it % npairs]);      // measured costs (calibrate_contract_costs)
         W1 += cost[it];
     }
     // block length (the period at which a CTA with several segments alternates between them): ~120 MB of Phi rows.
@@ -403,12 +409,13 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSc
     }
 }
 
-void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector<double>* item_frac) {
+void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector<double>* item_frac, const std::vector<double>* pair_cost = nullptr) {
     cudaStream_t st = h->stream;
     size_t max_segs = 0;
     for (int k = 0; k < 2; k++) {
         ContractSchedule S;
-        compute_contract_schedule(h->nbp, nchunk, nsm, k == 0 ? 2 : 1, S, item_frac);
+        compute_contract_schedule(h->nbp, nchunk, nsm, k == 0 ? 2 : 1, S, item_frac, pair_cost);
+        if (k == 1) h->host_sched = S;  // kept for the calibration pass
         h->npairs = S.npairs;
         h->con_bc = S.bc;
         if (k == 0) h->d_pairs.upload(S.pairs, st);
@@ -420,9 +427,88 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector
         D.cta_off.upload(S.cta_off, st);
         D.item_off.upload(S.item_off, st);
         max_segs = std::max(max_segs, S.segs.size());
+        if (std::getenv("DFTGRID_DEBUG_CTA_TIMES") && k == 1)  // developer instrumentation: the fused schedule's segments per CTA
+            for (int c = 0; c + 1 < (int)S.cta_off.size(); c++) {
+                std::fprintf(stderr, "[dftgrid] sched cta %3d:", c);
+                for (int q = S.cta_off[c]; q < S.cta_off[c + 1]; q++)
+                    std::fprintf(stderr, " (pair %d [%d,%d] share %.3f)", S.segs[q].pair, S.pairs[2 * S.segs[q].pair], S.pairs[2 * S.segs[q].pair + 1],
+                                 (S.segs[q].te - S.segs[q].tb) / 2147483648.0);
+                std::fprintf(stderr, "\n");
+            }
         CK(cudaStreamSynchronize(st));  // S goes out of scope
     }
     h->d_partial.alloc(max_segs * kTileM * kTileN);
+}
+
+// Measured cost model of the screened contraction.  The analytic weights (DMMA counts per tile kind x the map's work
+// fractions) miss what the map does to the memory side: a tile pair that is significant for few chunks is read by few
+// CTAs, its Phi rows come from DRAM instead of the L2 and its stages run latency-bound (measured on a 1/8 shard of
+// (H2O)64: 2.5 us per diagonal stage on near tiles, 3-4.3 us on far ones; CTAs with equal modelled shares differed by
+// 60 %).  So the schedule is calibrated on the device it will run on: one instrumented launch of the fused contraction
+// (per CTA: wall time and stages consumed), the time per staged chunk of every tile pair from the CTAs that hold a single
+// segment, and the stream-K shares are cut again on cost(pair) = P(chunk staged for the pair) x measured time per stage.
+// The launch costs as much as one contraction, once per grid.  Results do not depend on it (any schedule sums the same
+// partial tiles in a fixed order); DFTGRID_NO_CALIBRATE keeps the analytic model.
+void calibrate_contract_costs(dftgrid* h, int nsm, const std::vector<double>& sig_frac, const std::vector<double>& item_frac) {
+    if (std::getenv("DFTGRID_NO_CALIBRATE") || h->n_active_chunks < 4L * nsm) return;
+    cudaStream_t st = h->stream;
+    const dftgrid::DevSchedule& D = h->sched[1];
+    const ContractSchedule& S = h->host_sched;
+    const int npairs = S.npairs;
+    DevBuf<unsigned long long> d_times;
+    d_times.alloc(3 * (size_t)D.ctas);
+    std::vector<unsigned long long> t(3 * (size_t)D.ctas);
+    for (int rep = 0; rep < 2; rep++)  // the second launch runs at steady clocks with the schedule's own L2 pattern
+        k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dF.p, h->d_dF.p, h->d_con_chunk_ids.p, h->d_con_chunk_mask.p,
+                                                                         h->d_pairs.p, D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp,
+                                                                         (int)h->n_active_chunks, h->con_bc, d_times.p);
+    h->launches += 2;
+    CK(cudaMemcpyAsync(t.data(), d_times.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    // time per stage of every pair that some CTA holds alone
+    std::vector<std::vector<double>> samples(npairs);
+    for (int c = 0; c < D.ctas; c++) {
+        if (S.cta_off[c + 1] - S.cta_off[c] != 1) continue;
+        const double us = (double)(t[3 * c + 1] - t[3 * c]) * 1e-3;
+        const double stages = (double)(t[3 * c + 2] & 0xffffffffull);
+        if (stages >= 24.0 && us > 0.0) samples[S.segs[S.cta_off[c]].pair].push_back(us / stages);
+    }
+    // pairs without a sample: the analytic per-stage cost, scaled by the median measured / analytic ratio
+    std::vector<double> analytic(npairs), per_stage(npairs, 0.0);
+    for (int p = 0; p < npairs; p++) {
+        const double staged = std::max(sig_frac[p], 1e-6);
+        analytic[p] = item_frac[p] / staged;  // mean masked fraction of a staged chunk (floor included), relative units
+    }
+    std::vector<double> ratios;
+    for (int p = 0; p < npairs; p++)
+        if (!samples[p].empty()) {
+            std::sort(samples[p].begin(), samples[p].end());
+            per_stage[p] = samples[p][samples[p].size() / 2];
+        }
+    // analytic base cost per pair kind (same constants as compute_contract_schedule), to scale the unmeasured pairs
+    auto base_cost = [&](int p) {
+        const int ti = S.pairs[2 * p], tj = S.pairs[2 * p + 1];
+        const int wj = std::min(kTileN, h->nbp - tj * kTileN);
+        const bool narrow = wj <= 64, narrow32 = wj <= 32;
+        return ti == tj ? (narrow32 ? 5.0 : narrow ? 6.5 : 11.5) : (narrow32 ? 6.5 : narrow ? 10.5 : 20.0);
+    };
+    for (int p = 0; p < npairs; p++)
+        if (per_stage[p] > 0.0) ratios.push_back(per_stage[p] / (base_cost(p) * analytic[p]));
+    if (ratios.size() < 2) return;  // nothing reliable measured: keep the analytic schedule
+    std::sort(ratios.begin(), ratios.end());
+    const double r = ratios[ratios.size() / 2];
+    std::vector<double> pair_cost(npairs);
+    for (int p = 0; p < npairs; p++) {
+        const double ps = per_stage[p] > 0.0 ? per_stage[p] : r * base_cost(p) * analytic[p];
+        pair_cost[p] = sig_frac[p] * ps;  // mean cost of a chunk POSITION for the pair
+    }
+    if (std::getenv("DFTGRID_DEBUG_CTA_TIMES"))
+        for (int p = 0; p < npairs; p++)
+            std::fprintf(stderr, "[dftgrid] calibrated pair %d [%d,%d]: %.2f us/stage (%zu samples), staged %.3f, analytic %.3f\n", p, S.pairs[2 * p],
+                         S.pairs[2 * p + 1], per_stage[p], samples[p].size(), sig_frac[p], analytic[p]);
+    build_contract_schedule(h, h->n_active_chunks, nsm, nullptr, &pair_cost);
+    h->calibrated = true;
 }
 
 // Lists of the 32-point chunks / 128-point tiles of Phi that hold any non-zero amplitude (k_chunk_flags), and the
@@ -462,18 +548,27 @@ void build_active_lists(dftgrid* h, int nsm) {
     h->screened = screen;
     if (screen) h->d_chunk_mask.upload(act_masks, st);
     CK(cudaStreamSynchronize(st));
-    // The contraction sweeps the active chunks in a golden-ratio shuffled order when the map is in use: any window of
+    // The contraction sweeps the active chunks in a pseudo-randomly shuffled order when the map is in use: any window of
     // positions then holds chunks of all atoms and radii, every tile pair pays its AVERAGE cost per window, and the CTAs
     // (whose shares are equalised on those averages) keep passing over the Phi rows in step, which is what lets a row's
     // ~14 uses hit the L2.  (In atom-major order a pair is cheap far from its atoms and expensive near them; the CTAs
     // drift apart by thousands of chunks and DRAM reads triple: measured 6.5 -> 18 GB.)
-    std::vector<double> item_frac;
+    std::vector<double> item_frac, sig_frac;
     if (screen && h->n_active_chunks > 0) {
         const long n = h->n_active_chunks;
-        std::vector<std::pair<double, int>> key((size_t)n);
+        // (an integer mixing hash, NOT another golden-ratio sequence: the device's ownership hash of the POSITIONS is one, and
+        // the composition of two of them maps runs of neighbouring chunks — one atom's shells, exactly the chunks that are
+        // significant for a far tile pair — onto arithmetic progressions of owners: CTAs with equal shares of one item
+        // then differed by 60 % in work)
+        std::vector<std::pair<unsigned, int>> key((size_t)n);
         for (long k = 0; k < n; k++) {
-            const double f = (double)k * 0.6180339887498949;
-            key[k] = {f - std::floor(f), (int)k};
+            unsigned v = (unsigned)k * 0x9E3779B1u + 0x7F4A7C15u;
+            v ^= v >> 16;
+            v *= 0x85EBCA6Bu;
+            v ^= v >> 13;
+            v *= 0xC2B2AE35u;
+            v ^= v >> 16;
+            key[k] = {v, (int)k};
         }
         std::sort(key.begin(), key.end());
         std::vector<int> con_ids((size_t)n);
@@ -496,10 +591,12 @@ void build_active_lists(dftgrid* h, int nsm) {
             for (int tj = ti; tj < nt; tj++) {
                 const int nbj = std::min(4, nblk - 4 * tj);
                 double acc = 0.0;
+                long staged = 0;
                 for (long x = 0; x < n; x++) {
                     const unsigned long long cm = act_masks[x];
                     const unsigned ab = (unsigned)(cm >> (4 * ti)) & 0xFu, bb = (unsigned)(cm >> (4 * tj)) & ((1u << nbj) - 1u);
                     if (!ab || !bb) continue;
+                    staged++;
                     if (ti != tj) {
                         acc += std::max(floor_, (double)__builtin_popcount(bb) / nbj);
                     } else if (nbj == 4) {  // triangular diagonal tile: staged chunks run the full stage
@@ -509,6 +606,7 @@ void build_active_lists(dftgrid* h, int nsm) {
                     }
                 }
                 item_frac.push_back(acc / (double)n);
+                sig_frac.push_back((double)staged / (double)n);
             }
         double mean = 0.0;
         for (double f : item_frac) mean += f;
@@ -529,8 +627,9 @@ void build_active_lists(dftgrid* h, int nsm) {
         }
     }
     build_contract_schedule(h, h->n_active_chunks, nsm, item_frac.empty() ? nullptr : &item_frac);
+    if (!item_frac.empty()) calibrate_contract_costs(h, nsm, sig_frac, item_frac);
     if (std::getenv("DFTGRID_DEBUG_CTA_TIMES")) {
-        h->d_dbg_times.alloc(2 * (size_t)nsm + 2);
+        h->d_dbg_times.alloc(3 * (size_t)nsm + 3);
         for (size_t i = 0; i < item_frac.size(); i++) std::fprintf(stderr, "[dftgrid] pair %zu work fraction %.3f\n", i, item_frac[i]);
     }
 }
@@ -1057,13 +1156,15 @@ void run_contract(dftgrid* h, int mode) {
                                                                      h->screened ? h->d_con_chunk_mask.p : nullptr, h->d_pairs.p, D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc, h->d_dbg_times.p);
     if (h->d_dbg_times.p && !h->capturing) {
         // developer instrumentation: per-CTA wall time of the contraction with the CTA's segments
-        std::vector<unsigned long long> t(2 * (size_t)D.ctas);
+        std::vector<unsigned long long> t(3 * (size_t)D.ctas);
         CK(cudaMemcpyAsync(t.data(), h->d_dbg_times.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         unsigned long long t0 = ~0ull;
-        for (int c = 0; c < D.ctas; c++) t0 = std::min(t0, t[2 * c]);
-        std::fprintf(stderr, "[dftgrid] contraction CTA times (start us, duration us) mode %d\n", mode);
-        for (int c = 0; c < D.ctas; c++) std::fprintf(stderr, "  cta %3d  %8.1f %8.1f\n", c, (t[2 * c] - t0) * 1e-3, (t[2 * c + 1] - t[2 * c]) * 1e-3);
+        for (int c = 0; c < D.ctas; c++) t0 = std::min(t0, t[3 * c]);
+        std::fprintf(stderr, "[dftgrid] contraction CTA times (start us, duration us, stages) mode %d\n", mode);
+        for (int c = 0; c < D.ctas; c++)
+            std::fprintf(stderr, "  cta %3d  %8.1f %8.1f %6llu sm %llu\n", c, (t[3 * c] - t0) * 1e-3, (t[3 * c + 1] - t[3 * c]) * 1e-3,
+                         t[3 * c + 2] & 0xffffffffull, t[3 * c + 2] >> 32);
     }
     double* res = fock ? h->d_fres.p : h->d_res.p;
     if (h->peer_ready) {

@@ -361,7 +361,12 @@ __global__ void k_rho_combine(const double* __restrict__ part, long part_stride,
 // C_z = Phi^T diag(d_z) Phi  (upper-triangular 128x128 tile pairs, split over point ranges)
 // =========================================================================================================
 constexpr int kConMaskOff = 2 * kTileK * kLdN + kTileK;  // 8-byte slot after the weights: the staged chunk's block map
-constexpr int kConStageDoubles = kConMaskOff + 2;         // (+2 keeps every stage 16-byte aligned for the bulk copies)
+constexpr int kConFlagOff = kConMaskOff + 1;              // 8-byte slot: kConLast | kConEmpty
+constexpr int kConStageDoubles = kConMaskOff + 2;         // (every stage stays 16-byte aligned for the bulk copies)
+// Stage flags.  The producers mark the last stage of every (block, segment) group, so the DMMA warps need no chunk count
+// of their own (counting meant a scan of the ownership hash and the screening map per group, ~10 us of pipeline stall at
+// every switch of a multi-segment CTA); a group without any owned chunk is a data-less marker stage.
+constexpr unsigned long long kConLast = 1ull, kConEmpty = 2ull;
 
 // Warp tiling of the 128 x (128|64) output tile: 8 warps stacked along M, each owning MT = 2 row tiles (16 rows) and
 // the whole width (NT = 16 column tiles, 8 for an edge tile).  Per k4-step a warp then scales only 2 A fragments by the
@@ -504,32 +509,24 @@ __device__ __forceinline__ bool con_owns(const ConSeg& sg, int x, unsigned long 
 }
 __device__ __forceinline__ unsigned long long con_tile_bits(int t) { return 0xFull << (4 * t); }
 
-// Number of chunk positions of [x0, x1) owned by the segment (warp-collective, same value in every lane).
-__device__ __forceinline__ int con_count_owned(const ConSeg& sg, int x0, int x1, int lane, const unsigned long long* __restrict__ chunk_mask,
-                                               unsigned long long mi, unsigned long long mj) {
-    int cnt = 0;
-    for (int base = x0; base < x1; base += 32) {
-        const int x = base + lane;
-        const unsigned long long cm = (x < x1 && chunk_mask) ? chunk_mask[x] : ~0ull;
-        cnt += __popc(__ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x, cm, mi, mj)));
-    }
-    return cnt;
-}
-
 constexpr int kConTmaThreads = kDenseThreads + 128;  // 2 DMMA warpgroups + 1 producer warpgroup: warp 8 operand A, warp 9 operand B and the weights
 constexpr size_t kConTmaSmemBytes = (size_t)kStages * kConStageDoubles * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
 
 // The chunk loop of one segment for one DMMA warp; `op` consumes one staged chunk.
+// The stages of one (block, segment) group for one DMMA warp, up to and including the one flagged kConLast.
 template <class Op>
-__device__ __forceinline__ void con_run_segment(const double* sm, unsigned long long* full, unsigned long long* empty, int nchunks, unsigned& n,
-                                                int lane, Op&& op) {
-    for (int c = 0; c < nchunks; c++, n++) {
+__device__ __forceinline__ void con_run_group(const double* sm, unsigned long long* full, unsigned long long* empty, unsigned& n, int lane, Op&& op) {
+    for (;;) {
         const unsigned stage = n % kStages, round = n / kStages;
         mbar_wait(full + stage, round & 1u);
         stress_delay(2, n);
-        op(sm + (size_t)stage * kConStageDoubles);
+        const double* st = sm + (size_t)stage * kConStageDoubles;
+        const unsigned long long flags = *reinterpret_cast<const unsigned long long*>(st + kConFlagOff);
+        if (!(flags & kConEmpty)) op(st);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);
+        n++;
+        if (flags & kConLast) break;
     }
 }
 
@@ -723,14 +720,11 @@ __device__ __forceinline__ void con_segment_blocks_mode(const double* sm, unsign
     } else {
         Mode::template io<true>(out, acc, warp, lane);
     }
-    {
-        const int x0 = min(b_begin * bc, nchunk), x1 = min(b_end * bc, nchunk);
-        con_run_segment(sm, full, empty, con_count_owned(sg, x0, x1, lane, chunk_mask, con_tile_bits(ti), con_tile_bits(tj)), n, lane,
-                        [&](const double* st) {
-                            const unsigned long long cm = *reinterpret_cast<const unsigned long long*>(st + kConMaskOff);
-                            Mode::mma(st, acc, warp, lane, (unsigned)(cm >> (4 * ti)) & 0xFu, (unsigned)(cm >> (4 * tj)) & 0xFu);
-                        });
-    }
+    for (int b = b_begin; b < b_end; b++)  // one group per block; the producers flag each group's last stage
+        con_run_group(sm, full, empty, n, lane, [&](const double* st) {
+            const unsigned long long cm = *reinterpret_cast<const unsigned long long*>(st + kConMaskOff);
+            Mode::mma(st, acc, warp, lane, (unsigned)(cm >> (4 * ti)) & 0xFu, (unsigned)(cm >> (4 * tj)) & 0xFu);
+        });
     Mode::template io<false>(out, acc, warp, lane);
 }
 
@@ -811,6 +805,36 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
                 const unsigned bytes = prodA ? kTileK * wi : kTileK * (diag ? 0u : wj) + kTileK * 8u;
                 const int x0 = min(b * bc, nchunk), x1 = min((b + 1) * bc, nchunk);
                 const unsigned long long mi = con_tile_bits(ti), mj = con_tile_bits(tj);
+                // one stage: wait for the slot, publish map + flags, copy (a marker stage carries no data)
+                auto emit = [&](size_t row0, unsigned long long cmx, unsigned long long flags) {
+                    const unsigned stage = n % kStages, round = n / kStages;
+                    double* st = sm + (size_t)stage * kConStageDoubles;
+                    const bool data = !(flags & kConEmpty);
+                    stress_delay(1, n);
+                    mbar_wait(empty + stage, (round & 1u) ^ 1u);
+                    if (lane == 0) {
+                        if (prodA) {  // plain stores, released by the arrive below
+                            *reinterpret_cast<unsigned long long*>(st + kConMaskOff) = cmx;
+                            *reinterpret_cast<unsigned long long*>(st + kConFlagOff) = flags;
+                        }
+                        mbar_arrive_expect_tx(full + stage, data ? bytes : 0u);
+                    }
+                    __syncwarp();
+                    if (data) {
+                        const double* row = phi + (row0 + lane) * (size_t)nbp;
+                        if (prodA) {
+                            bulk_copy_g2s(st + lane * kLdN, row + ci, wi, full + stage);
+                        } else {
+                            if (!diag) bulk_copy_g2s(st + kTileK * kLdN + lane * kLdN, row + cj, wj, full + stage);
+                            if (lane == 0) bulk_copy_g2s(st + 2 * kTileK * kLdN, d + row0, kTileK * 8u, full + stage);
+                        }
+                    }
+                    n++;
+                };
+                // the group's owned chunks are emitted one behind the scan, so that the last one can carry kConLast
+                bool have = false;
+                size_t pend_row0 = 0;
+                unsigned long long pend_cm = 0ull;
                 for (int base = x0; base < x1; base += 32) {
                     const int x = base + lane;
                     const unsigned long long cm = (x < x1 && chunk_mask) ? chunk_mask[x] : ~0ull;
@@ -821,26 +845,13 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
                         mask &= mask - 1u;
                         const size_t row0 = (size_t)__shfl_sync(0xffffffffu, my_chunk, src) * kTileK;
                         const unsigned long long cmx = __shfl_sync(0xffffffffu, cm, src);
-                        const unsigned stage = n % kStages, round = n / kStages;
-                        double* st = sm + (size_t)stage * kConStageDoubles;
-                        stress_delay(1, n);
-                        mbar_wait(empty + stage, (round & 1u) ^ 1u);
-                        if (lane == 0) {
-                            // the chunk's block map travels with the stage (plain store, released by the arrive below)
-                            if (prodA) *reinterpret_cast<unsigned long long*>(st + kConMaskOff) = cmx;
-                            mbar_arrive_expect_tx(full + stage, bytes);
-                        }
-                        __syncwarp();
-                        const double* row = phi + (row0 + lane) * (size_t)nbp;
-                        if (prodA) {
-                            bulk_copy_g2s(st + lane * kLdN, row + ci, wi, full + stage);
-                        } else {
-                            if (!diag) bulk_copy_g2s(st + kTileK * kLdN + lane * kLdN, row + cj, wj, full + stage);
-                            if (lane == 0) bulk_copy_g2s(st + 2 * kTileK * kLdN, d + row0, kTileK * 8u, full + stage);
-                        }
-                        n++;
+                        if (have) emit(pend_row0, pend_cm, 0ull);
+                        pend_row0 = row0;
+                        pend_cm = cmx;
+                        have = true;
                     }
                 }
+                emit(pend_row0, pend_cm, have ? kConLast : (kConLast | kConEmpty));
             }
         }
         return;
@@ -869,8 +880,11 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
     if (dbg_times && tid == 0) {  // developer instrumentation (DFTGRID_DEBUG_CTA_TIMES): wall time of this CTA's DMMA warps
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
-        dbg_times[2 * blockIdx.x] = dbg_t0;
-        dbg_times[2 * blockIdx.x + 1] = t1;
+        dbg_times[3 * blockIdx.x] = dbg_t0;
+        dbg_times[3 * blockIdx.x + 1] = t1;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;\n" : "=r"(smid));
+        dbg_times[3 * blockIdx.x + 2] = (unsigned long long)n | ((unsigned long long)smid << 32);  // stages consumed | SM id
     }
 }
 

@@ -10,9 +10,13 @@ name = sys.argv[1] if len(sys.argv) > 1 else "h2o64"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 fac, prm = WORKLOADS[name]
 mol = fac()
-g = MolecularGrid(mol)
+rank, nranks = int(os.environ.get("FAKE_RANK", "0")), int(os.environ.get("FAKE_NRANKS", "1"))
+if nranks > 1:
+    os.environ["DFTGRID_DEBUG_SKIP_COMM"] = "1"  # time one shard's kernels on a single GPU (results are partial sums)
+g = MolecularGrid(mol, rank=rank, nranks=nranks)
 g.set_grid_parameters(*prm)
-g.create_grid()
+g.create_grid(comm_id=False if nranks > 1 else None)
+print("rank", rank, "of", nranks, "local points", g.nloc, "offset", g.point_offset)
 P = synthetic_density(mol)
 os.environ["DFTGRID_NO_GRAPH"] = "1"
 for _ in range(n):
