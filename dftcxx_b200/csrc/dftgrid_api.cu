@@ -452,63 +452,88 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector
 void calibrate_contract_costs(dftgrid* h, int nsm, const std::vector<double>& sig_frac, const std::vector<double>& item_frac) {
     if (std::getenv("DFTGRID_NO_CALIBRATE") || h->n_active_chunks < 4L * nsm) return;
     cudaStream_t st = h->stream;
-    const dftgrid::DevSchedule& D = h->sched[1];
-    const ContractSchedule& S = h->host_sched;
-    const int npairs = S.npairs;
-    DevBuf<unsigned long long> d_times;
-    d_times.alloc(3 * (size_t)D.ctas);
-    std::vector<unsigned long long> t(3 * (size_t)D.ctas);
-    for (int rep = 0; rep < 2; rep++)  // the second launch runs at steady clocks with the schedule's own L2 pattern
-        k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dF.p, h->d_dF.p, h->d_con_chunk_ids.p, h->d_con_chunk_mask.p,
-                                                                         h->d_pairs.p, D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp,
-                                                                         (int)h->n_active_chunks, h->con_bc, d_times.p);
-    h->launches += 2;
-    CK(cudaMemcpyAsync(t.data(), d_times.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    // time per stage of every pair that some CTA holds alone
-    std::vector<std::vector<double>> samples(npairs);
-    for (int c = 0; c < D.ctas; c++) {
-        if (S.cta_off[c + 1] - S.cta_off[c] != 1) continue;
-        const double us = (double)(t[3 * c + 1] - t[3 * c]) * 1e-3;
-        const double stages = (double)(t[3 * c + 2] & 0xffffffffull);
-        if (stages >= 24.0 && us > 0.0) samples[S.segs[S.cta_off[c]].pair].push_back(us / stages);
-    }
-    // pairs without a sample: the analytic per-stage cost, scaled by the median measured / analytic ratio
-    std::vector<double> analytic(npairs), per_stage(npairs, 0.0);
-    for (int p = 0; p < npairs; p++) {
-        const double staged = std::max(sig_frac[p], 1e-6);
-        analytic[p] = item_frac[p] / staged;  // mean masked fraction of a staged chunk (floor included), relative units
-    }
-    std::vector<double> ratios;
-    for (int p = 0; p < npairs; p++)
-        if (!samples[p].empty()) {
-            std::sort(samples[p].begin(), samples[p].end());
-            per_stage[p] = samples[p][samples[p].size() / 2];
+    const bool verbose = std::getenv("DFTGRID_DEBUG_CTA_TIMES") != nullptr;
+    // one instrumented run of the CURRENT fused schedule: kernel span in us, per-CTA (duration us, stages)
+    auto measure = [&](std::vector<double>& us, std::vector<double>& stages) -> double {
+        const dftgrid::DevSchedule& D = h->sched[1];
+        DevBuf<unsigned long long> d_times;
+        d_times.alloc(3 * (size_t)D.ctas);
+        std::vector<unsigned long long> t(3 * (size_t)D.ctas);
+        for (int rep = 0; rep < 2; rep++)  // the second launch runs at steady clocks with the schedule's own L2 pattern
+            k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, h->d_dF.p, h->d_dF.p, h->d_con_chunk_ids.p,
+                                                                             h->d_con_chunk_mask.p, h->d_pairs.p, D.segs.p, D.cta_off.p, h->d_partial.p,
+                                                                             h->nbp, (int)h->n_active_chunks, h->con_bc, d_times.p);
+        h->launches += 2;
+        CK(cudaMemcpyAsync(t.data(), d_times.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        unsigned long long t0 = ~0ull, t1 = 0ull;
+        us.assign(D.ctas, 0.0);
+        stages.assign(D.ctas, 0.0);
+        for (int c = 0; c < D.ctas; c++) {
+            t0 = std::min(t0, t[3 * c]);
+            t1 = std::max(t1, t[3 * c + 1]);
+            us[c] = (double)(t[3 * c + 1] - t[3 * c]) * 1e-3;
+            stages[c] = (double)(t[3 * c + 2] & 0xffffffffull);
         }
-    // analytic base cost per pair kind (same constants as compute_contract_schedule), to scale the unmeasured pairs
-    auto base_cost = [&](int p) {
+        return (double)(t1 - t0) * 1e-3;
+    };
+    auto base_cost = [&](const ContractSchedule& S, int p) {  // the analytic constants of compute_contract_schedule
         const int ti = S.pairs[2 * p], tj = S.pairs[2 * p + 1];
         const int wj = std::min(kTileN, h->nbp - tj * kTileN);
         const bool narrow = wj <= 64, narrow32 = wj <= 32;
         return ti == tj ? (narrow32 ? 5.0 : narrow ? 6.5 : 11.5) : (narrow32 ? 6.5 : narrow ? 10.5 : 20.0);
     };
-    for (int p = 0; p < npairs; p++)
-        if (per_stage[p] > 0.0) ratios.push_back(per_stage[p] / (base_cost(p) * analytic[p]));
-    if (ratios.size() < 2) return;  // nothing reliable measured: keep the analytic schedule
-    std::sort(ratios.begin(), ratios.end());
-    const double r = ratios[ratios.size() / 2];
-    std::vector<double> pair_cost(npairs);
-    for (int p = 0; p < npairs; p++) {
-        const double ps = per_stage[p] > 0.0 ? per_stage[p] : r * base_cost(p) * analytic[p];
-        pair_cost[p] = sig_frac[p] * ps;  // mean cost of a chunk POSITION for the pair
+    // costs from a measurement of the current schedule; empty when nothing reliable was measured
+    auto costs_from = [&](const std::vector<double>& us, const std::vector<double>& stages) {
+        const ContractSchedule& S = h->host_sched;
+        const int npairs = S.npairs;
+        std::vector<std::vector<double>> samples(npairs);
+        for (int c = 0; c + 1 < (int)S.cta_off.size(); c++)
+            if (S.cta_off[c + 1] - S.cta_off[c] == 1 && stages[c] >= 24.0 && us[c] > 0.0) samples[S.segs[S.cta_off[c]].pair].push_back(us[c] / stages[c]);
+        std::vector<double> per_stage(npairs, 0.0), analytic(npairs), ratios;
+        for (int p = 0; p < npairs; p++) {
+            analytic[p] = item_frac[p] / std::max(sig_frac[p], 1e-6);  // mean masked fraction of a staged chunk
+            if (!samples[p].empty()) {
+                std::sort(samples[p].begin(), samples[p].end());
+                per_stage[p] = samples[p][samples[p].size() / 2];
+                ratios.push_back(per_stage[p] / (base_cost(S, p) * analytic[p]));
+            }
+        }
+        std::vector<double> pair_cost;
+        if (ratios.size() < 2) return pair_cost;
+        std::sort(ratios.begin(), ratios.end());
+        const double r = ratios[ratios.size() / 2];  // unmeasured pairs: the analytic cost at the median measured / analytic ratio
+        pair_cost.resize(npairs);
+        for (int p = 0; p < npairs; p++) pair_cost[p] = sig_frac[p] * (per_stage[p] > 0.0 ? per_stage[p] : r * base_cost(S, p) * analytic[p]);
+        if (verbose)
+            for (int p = 0; p < npairs; p++)
+                std::fprintf(stderr, "[dftgrid] calibrated pair %d [%d,%d]: %.2f us/stage (%zu samples), staged %.3f\n", p, S.pairs[2 * p], S.pairs[2 * p + 1],
+                             per_stage[p], samples[p].size(), sig_frac[p]);
+        return pair_cost;
+    };
+    // Autotuning loop: the analytic schedule, then up to two schedules cut on what the previous one measured; the fastest
+    // measured schedule is kept (a re-cut is not always a gain: the CTAs at item boundaries and their SM-pair neighbours
+    // carry overheads that are not a property of the pair).
+    std::vector<double> us, stages, best_cost, cur_cost;
+    double best = measure(us, stages);
+    if (verbose) std::fprintf(stderr, "[dftgrid] contraction schedule, analytic costs: %.1f us\n", best);
+    for (int round = 0; round < 2; round++) {
+        cur_cost = costs_from(us, stages);
+        if (cur_cost.empty()) break;
+        build_contract_schedule(h, h->n_active_chunks, nsm, nullptr, &cur_cost);
+        const double tcur = measure(us, stages);
+        if (verbose) std::fprintf(stderr, "[dftgrid] contraction schedule, measured costs (round %d): %.1f us\n", round + 1, tcur);
+        if (tcur < 0.98 * best) {
+            best = tcur;
+            best_cost = cur_cost;
+        }
     }
-    if (std::getenv("DFTGRID_DEBUG_CTA_TIMES"))
-        for (int p = 0; p < npairs; p++)
-            std::fprintf(stderr, "[dftgrid] calibrated pair %d [%d,%d]: %.2f us/stage (%zu samples), staged %.3f, analytic %.3f\n", p, S.pairs[2 * p],
-                         S.pairs[2 * p + 1], per_stage[p], samples[p].size(), sig_frac[p], analytic[p]);
-    build_contract_schedule(h, h->n_active_chunks, nsm, nullptr, &pair_cost);
-    h->calibrated = true;
+    if (best_cost.empty())
+        build_contract_schedule(h, h->n_active_chunks, nsm, &item_frac);
+    else
+        build_contract_schedule(h, h->n_active_chunks, nsm, nullptr, &best_cost);
+    h->calibrated = !best_cost.empty();
 }
 
 // Lists of the 32-point chunks / 128-point tiles of Phi that hold any non-zero amplitude (k_chunk_flags), and the
