@@ -426,6 +426,7 @@ def main():
     e2e_ms = max_over_ranks(e2e_ms)
     clocks = sampler.stop() if sampler else None
 
+    screen_frac = g.screen_fraction()
     # ---- roofline of the dominant kernel (the DMMA contraction of F_grid), live event timings of the last fused step
     npts_loc = g.npoints / ngpus_total  # the mean shard (shards are cut at equal estimated work, not equal point counts)
     flops_contract = 1.0 * npts_loc * mol.nbf * (mol.nbf + 1)  # one symmetric matrix: Npts*nb*(nb+1) flop
@@ -438,6 +439,10 @@ def main():
             "peak_source": "FP64 DMMA peak measured on this pool with tools/microbench/fp64_peak.cu (MEASURED_PEAKS.json has no FP64 entry; "
                            "its HBM figure %s GB/s is the denominator for the streaming kernels, %s)" % (peaks.get("hbm_gbs"), peak_kind),
             "ms": con_ms,
+            "screen_work_fraction": screen_frac,
+            "note": "achieved = ALGORITHMIC flops Npts*nb*(nb+1) / time; the block map of Phi lets the kernel skip insignificant 32-column "
+                    "blocks (|phi| <= 1e-20), so it executes about screen_work_fraction of them and frac can exceed what a dense evaluation "
+                    "reaches (dense: 10.5 ms = 0.999 at (H2O)64, DMMA pipe 92.7 % busy, profiles/r02_*)",
             "second_kernel": {"kernel": "k_rho_tma", "ms": rho_ms, "achieved_full_2Nnb2": 2.0 * npts_loc * mol.nbf ** 2 / (rho_ms * 1e-3) / 1e12 if rho_ms > 0 else None,
                               "note": "executes half of 2*Npts*nb^2 (P symmetric): frac of peak on executed flops = achieved/2/peak"}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
