@@ -718,7 +718,7 @@ void build_pair_bins(dftgrid* h) {
 // This rank's contiguous block of the (atom, radial shell) units.  With screening the tensor work of a shell depends on
 // how many 32-column blocks of Phi are significant on it (a shell far from most atoms is cheap), so equal shell COUNTS
 // (dftgrid_shard_range) leave the ranks up to ~20 % out of balance; the blocks are therefore cut at equal estimated WORK:
-//   w(shell) = (significant blocks / blocks)^2 [rho and the contraction] + 0.25 [interpolation, pointwise work]
+//   w(shell) = t_dense (f^2 [rho] + f [contraction]) + t_interp [interpolation],  f = significant blocks / blocks
 // where a block counts as significant on shell (a, r) when some basis function f in it has | |R_a - R_f| - r | < reach_f,
 // reach_f = the distance beyond which |phi_f| <= tau by the bound sum_k |c_k N_k| d^L exp(-alpha_k d^2).  Pure host
 // arithmetic on replicated data: every rank computes the same cuts.  Single rank, or screening off: the plain rule.
@@ -745,6 +745,12 @@ void shard_shells(dftgrid* h, const std::vector<double>& rtab, long nshell, long
         reach[f] = rf;
     }
     const int nrad = h->prm.radial_points, na = h->natoms;
+    // per-point cost model (ns, B200): the density kernel executes nb^2 DMMA flops per point on the significant blocks
+    // (~ fsig^2), the fused contraction nb (nb + 1) of which screening removes less (masked stages have a floor, diagonal
+    // tiles run whole: ~ fsig, measured on the shards of (H2O)64), the interpolation 6.2 FP64 operations per
+    // (point, source atom, lm) at ~70 % of the FP64 pipe whatever the map says
+    const int lmax = h->prm.lmax, nlm = (lmax + 1) * (lmax + 1);
+    const double t_dense = (double)h->nbf * h->nbf / 37.0e3, t_interp = (double)(na - 1) * nlm * 6.2 / 13.0e3;
     std::vector<double> cum((size_t)nshell + 1, 0.0);
     std::vector<double> dist(h->nbf);
     for (int a = 0; a < na; a++) {
@@ -761,7 +767,7 @@ void shard_shells(dftgrid* h, const std::vector<double>& rtab, long nshell, long
                 nsig += sig ? 1 : 0;
             }
             const double fsig = (double)nsig / nblk;
-            cum[(size_t)a * nrad + i + 1] = cum[(size_t)a * nrad + i] + fsig * fsig + 0.25;
+            cum[(size_t)a * nrad + i + 1] = cum[(size_t)a * nrad + i] + t_dense * (fsig * fsig + fsig) + t_interp;
         }
     }
     const double total = cum[nshell];
