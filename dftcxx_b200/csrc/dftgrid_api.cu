@@ -24,6 +24,7 @@
 #include "kernels_grid.cuh"
 #include "kernels_hartree.cuh"
 #include "kernels_peer.cuh"
+#include "kernels_rect.cuh"
 #include "kernels_scf.cuh"
 #include "nccl_dyn.h"
 
@@ -2201,6 +2202,54 @@ int dftgrid_get_amplitudes(dftgrid_t* h, double* phi) {
         CK(cudaStreamSynchronize(h->stream));
     });
 }
+// RectangularGrid::build_grid + set_density (src/rectangulargrid.cpp:34-80): density and density gradient on a dp^3 box
+static void launch_rect(dftgrid* h, int PT, const double* dP, double size, int dp, long npts, double* dpos, double* drho, double* dgrad) {
+    const size_t smem = (size_t)4 * PT * h->nbf * sizeof(double);
+    const unsigned grid = (unsigned)((npts + PT - 1) / PT);
+#define DFG_RECT_LAUNCH(N)                                                                                                          \
+    CK(cudaFuncSetAttribute(k_rect_density<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                              \
+    k_rect_density<N><<<grid, kRectThreads, smem, h->stream>>>(h->nbf, h->d_bf_center.p, h->d_bf_prim_off.p, h->d_center_xyz.p,        \
+                                                               h->d_prim_exp.p, h->d_exp_alpha.p, h->d_prim_coeff.p, h->d_prim_norm.p, \
+                                                               h->d_prim_lmn.p, dP, size, dp, npts, dpos, drho, dgrad)
+    if (PT == 4) {
+        DFG_RECT_LAUNCH(4);
+    } else if (PT == 2) {
+        DFG_RECT_LAUNCH(2);
+    } else {
+        DFG_RECT_LAUNCH(1);
+    }
+#undef DFG_RECT_LAUNCH
+    h->launches++;
+}
+
+int dftgrid_rectangular_density(dftgrid_t* h, double size, int dp, const double* P, double* pos, double* rho, double* grad) {
+    if (h->group) return dftgrid_rectangular_density(h->group->subs[0], size, dp, P, pos, rho, grad);
+    return guarded([&] {
+        use_device(h);
+        if (!h->built) throw std::runtime_error("dftgrid_build must be called before dftgrid_rectangular_density");
+        if (!P) throw std::runtime_error("null density matrix");
+        if (dp < 2 || dp > 1024 || !(size > 0.0)) throw std::runtime_error("rectangular grid: need size > 0 and 2 <= dp <= 1024");
+        const long npts = (long)dp * dp * dp;
+        const size_t nb2 = (size_t)h->nbf * h->nbf;
+        DevBuf<double> dP, dpos, drho, dgrad;
+        dP.alloc(nb2);
+        dpos.alloc(3 * (size_t)npts);
+        drho.alloc((size_t)npts);
+        dgrad.alloc(3 * (size_t)npts);
+        CK(cudaMemcpyAsync(dP.p, P, nb2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        const size_t per_point = (size_t)4 * h->nbf * sizeof(double), limit = 200u << 10;
+        if (per_point <= limit)
+            launch_rect(h, 4 * per_point <= limit ? 4 : (2 * per_point <= limit ? 2 : 1), dP.p, size, dp, npts, dpos.p, drho.p, dgrad.p);
+        else
+            throw std::runtime_error("rectangular grid: basis too large for the shared-memory staging (nbf > 6400)");
+        CK(cudaGetLastError());
+        if (pos) CK(cudaMemcpyAsync(pos, dpos.p, 3 * (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (rho) CK(cudaMemcpyAsync(rho, drho.p, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (grad) CK(cudaMemcpyAsync(grad, dgrad.p, 3 * (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    });
+}
+
 int dftgrid_get_rho_lm(dftgrid_t* h, double* out) {
     if (h->group) return dftgrid_get_rho_lm(h->group->subs[0], out);
     return guarded([&] {

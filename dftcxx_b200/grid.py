@@ -75,6 +75,7 @@ def lib():
     L.dftgrid_iteration.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp]
     L.dftgrid_download_results.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     L.dftgrid_last_timings.argtypes = [C.c_void_p, _dp, C.c_int]
+    L.dftgrid_rectangular_density.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, _dp, _dp, _dp]
     _lib = L
     return L
 
@@ -349,6 +350,14 @@ class MolecularGrid:
 
     def get_U_lm(self):
         return self._vec(lib().dftgrid_get_U_lm, (self.natoms, self.radial_points, self.nlm))
+
+    def rectangular_density(self, size, dp, P):
+        """RectangularGrid::build_grid(size, dp) + set_density(P) (src/rectangulargrid.cpp:34-80): positions [dp^3][3], density
+        [dp^3] and density gradient [dp^3][3] on a box of edge `size` centred at the origin of the molecule's frame."""
+        n = int(dp) ** 3
+        pos, rho, grad = np.zeros((n, 3)), np.zeros(n), np.zeros((n, 3))
+        self._ck(lib().dftgrid_rectangular_density(self.h, float(size), int(dp), _ptr(self._mat(P)), _ptr(pos), _ptr(rho), _ptr(grad)))
+        return pos, rho, grad
 
     def timings(self):
         t = np.zeros(len(T_NAMES))

@@ -112,5 +112,22 @@ int dfthost_sym_eigen(int n, const double* A, double* w, double* Vout) {
     }
 }
 
+// host-only: the engine keys of an input file (Settings): out = { gpus, scf mode, density_dump present, density_dump_size,
+// density_dump_points }.  Returns 0 or < 0.
+int dfthost_settings(const char* infile, double* out5) {
+    try {
+        dftcxx::Settings st(infile);
+        out5[0] = st.get_gpus();
+        out5[1] = st.get_scf_mode();
+        out5[2] = st.has("density_dump") ? 1.0 : 0.0;
+        out5[3] = st.get_density_dump_size();
+        out5[4] = st.get_density_dump_points();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
 void dfthost_boys(int nmax, double x, double* F) { dftcxx::Integrator::boys(nmax, x, F); }
 }

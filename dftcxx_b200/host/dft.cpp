@@ -1,5 +1,7 @@
 #include "dft.hpp"
 
+#include "rectangulargrid.hpp"
+
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -252,6 +254,21 @@ void DFT::scf(unsigned int max_iterations, double threshold) {
         std::cout << "========================================" << std::endl;
         std::cout << "Stopping because energy criterion is reached." << std::endl << std::endl;
     }
+    finalize();
+}
+
+// The reference's finalize (src/dft.cpp:489-504) holds the density dump as commented-out code "needs to be connected to
+// interface": RectangularGrid rg(mol); rg.build_grid(5.0, 15); rg.set_density(P); rg.write_gradient("data.dat").  Here it is
+// connected to the input file: `density_dump = <file>` switches it on (stock inputs have no such key and run unchanged),
+// `density_dump_size` (default 5.0) and `density_dump_points` (default 15) are the two build_grid arguments.
+void DFT::finalize() {
+    if (!settings->has("density_dump")) return;
+    const std::string file = settings->get_value("density_dump");
+    RectangularGrid rg(*molgrid);
+    rg.build_grid(settings->get_density_dump_size(), settings->get_density_dump_points());
+    rg.set_density(density_matrix());
+    rg.write_gradient(file);
+    if (verbose) std::cout << "Density gradient on a " << settings->get_density_dump_points() << "^3 grid written to " << file << std::endl << std::endl;
 }
 
 }  // namespace dftcxx

@@ -50,6 +50,7 @@ private:
     void calculate_electronic_repulsion_matrix();
     void calculate_exchange_correlation_matrix();
     void calculate_energy();
+    void finalize();  // density dump on a rectangular grid when the input asks for one (src/dft.cpp:489-504)
 
     std::shared_ptr<Settings> settings;
     std::shared_ptr<Molecule> mol;

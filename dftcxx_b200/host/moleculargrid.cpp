@@ -127,6 +127,10 @@ Mat MolecularGrid::scf_matrix(int which) const {
     return M;
 }
 
+void MolecularGrid::rectangular_density(double size, unsigned int dp, const Mat& P, double* pos, double* rho, double* grad) {
+    check(dftgrid_rectangular_density(handle, size, (int)dp, P.data(), pos, rho, grad));
+}
+
 int MolecularGrid::gpus() const { return handle ? dftgrid_ngpus(handle) : ngpus; }
 
 std::vector<double> MolecularGrid::get_weights() const {

@@ -106,6 +106,12 @@ void Settings::set_default_settings() {
     if (has("lebedev_order") && parse_uint(get_value("lebedev_order"), v)) lebedev_order = v;
     if (has("lmax") && parse_uint(get_value("lmax"), v)) lmax = v;
     if (has("gpus") && parse_uint(get_value("gpus"), v) && v >= 1) gpus = v;
+    if (has("density_dump_points") && parse_uint(get_value("density_dump_points"), v) && v >= 2) dump_points = v;
+    if (has("density_dump_size")) {
+        const double sz = parse_double(get_value("density_dump_size"));
+        if (!(sz > 0.0)) throw std::runtime_error("density_dump_size must be positive");
+        dump_size = sz;
+    }
     const std::string scf = has("scf") ? get_value("scf") : "device";
     const std::string fock = has("fock") ? get_value("fock") : "fused";
     scf_mode = scf == "host" ? (fock == "separate" ? (unsigned)SCF_HOST_SEPARATE : (unsigned)SCF_HOST_FUSED) : (unsigned)SCF_DEVICE;

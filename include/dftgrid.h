@@ -180,6 +180,14 @@ int dftgrid_get_potential(dftgrid_t* h, double* V /* [nloc] Hartree potential */
 int dftgrid_get_rho_lm(dftgrid_t* h, double* rho_lm /* [natoms][nrad][nlm] */);
 int dftgrid_get_U_lm(dftgrid_t* h, double* U_lm /* [natoms][nrad][nlm] */);
 
+/* RectangularGrid::build_grid(size, dp) + set_density(P) (src/rectangulargrid.cpp:34-80) — the data DFT::finalize's density
+ * dump writes (src/dft.cpp:489-504, commented out in the reference "needs to be connected to interface"): dp^3 points,
+ * point (i, j, k) at index (i*dp + j)*dp + k and position ((k, j, i) * size/(dp-1) - size/2) in the molecule's frame,
+ * rho = 2 phi^T P phi (src/gridpoint.cpp:82-84) and the density gradient of GridPoint::set_gradient (src/gridpoint.cpp:94-109)
+ * with the basis-function gradients exactly as CGF::get_grad evaluates them (src/cgf.cpp:67-94, 164-172).  Needs a built
+ * handle (device basis tables); any of pos [n][3], rho [n], grad [n][3] may be NULL. */
+int dftgrid_rectangular_density(dftgrid_t* h, double size, int dp, const double* P, double* pos, double* rho, double* grad);
+
 /* Per-phase device times (CUDA events on the handle's stream) of the most recent build / iteration, in ms.
  * Slots: see DFTGRID_T_* below.  n = number of doubles available in out. */
 int dftgrid_last_timings(dftgrid_t* h, double* out, int n);

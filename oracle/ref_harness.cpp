@@ -289,6 +289,43 @@ void ref_xc(refdft* h, double* XC, double* exc) {
     if (exc) *exc = h->exc_gridonly;
 }
 
+// RectangularGrid::build_grid(size, dp) + set_density(P) (src/rectangulargrid.cpp:34-80): the data behind the density dump of
+// DFT::finalize (src/dft.cpp:489-504).  pos [dp^3][3], rho [dp^3], grad [dp^3][3], in the reference's own point order.
+int ref_rect_density(refdft* h, double size, int dp, const double* P, double* pos, double* rho, double* grad) {
+    try {
+        RectangularGrid rg(h->mol);
+        rg.build_grid(size, (unsigned)dp);
+        rg.set_density(to_mat(P, h->m()->get_nr_bfs()));
+        for (size_t i = 0; i < rg.grid.size(); i++) {
+            const vec3& r = rg.grid[i].get_position();
+            const vec3& g = rg.grid[i].get_gradient();
+            for (int c = 0; c < 3; c++) {
+                pos[3 * i + c] = r[c];
+                grad[3 * i + c] = g[c];
+            }
+            rho[i] = rg.grid[i].get_density();
+        }
+        return (int)rg.grid.size();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// the reference's own writer (RectangularGrid::write_gradient, src/rectangulargrid.cpp:82-95) for the same grid
+int ref_rect_write(refdft* h, double size, int dp, const double* P, const char* filename) {
+    try {
+        RectangularGrid rg(h->mol);
+        rg.build_grid(size, (unsigned)dp);
+        rg.set_density(to_mat(P, h->m()->get_nr_bfs()));
+        rg.write_gradient(filename);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
 // pointwise functional values straight from the reference's Functional (src/functionals.cpp:24-114)
 void ref_functional(const double* rho, long n, double* ex, double* vx, double* ec, double* vc) {
     VectorXd d(n);

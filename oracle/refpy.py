@@ -62,6 +62,10 @@ def _lib(fast=False):
     L.ref_get_energies.restype = C.c_int
     L.ref_scf_step.argtypes = [C.c_void_p]
     L.ref_scf_step.restype = C.c_double
+    L.ref_rect_density.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, _dp, _dp, _dp]
+    L.ref_rect_density.restype = C.c_int
+    L.ref_rect_write.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, C.c_char_p]
+    L.ref_rect_write.restype = C.c_int
     L.ref_time_iteration.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp]
     L.ref_time_iteration.restype = C.c_double
     _libs[fast] = L
@@ -136,6 +140,21 @@ class Ref:
         rho = np.zeros(self.npts)
         self.L.ref_get_densities(self.h, _p(rho))
         return rho
+
+    def rect_density(self, size, dp, P):
+        """RectangularGrid::build_grid(size, dp) + set_density(P): positions [n][3], rho [n], gradient [n][3]."""
+        P = np.asfortranarray(P, dtype=np.float64)
+        n = dp ** 3
+        pos, rho, grad = np.zeros((n, 3)), np.zeros(n), np.zeros((n, 3))
+        if self.L.ref_rect_density(self.h, float(size), int(dp), P.ctypes.data_as(_dp), _p(pos), _p(rho), _p(grad)) != n:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        return pos, rho, grad
+
+    def rect_write(self, size, dp, P, filename):
+        """RectangularGrid::write_gradient: the reference's own dump file for the same grid."""
+        P = np.asfortranarray(P, dtype=np.float64)
+        if self.L.ref_rect_write(self.h, float(size), int(dp), P.ctypes.data_as(_dp), filename.encode()) != 0:
+            raise RuntimeError(self.L.ref_last_error().decode())
 
     def electron_count(self):
         return self.L.ref_electron_count(self.h)

@@ -199,6 +199,23 @@ def test_host_one_electron_integrals_match_reference(name):
     assert np.max(np.abs(S - S.T)) < 1e-15
 
 
+def test_host_settings_engine_keys(tmp_path):
+    """Keys the B200 host adds to the reference's input format; stock inputs (none of them present) keep the defaults."""
+    L, dp = _hostlib()
+    L.dfthost_settings.argtypes = [ctypes.c_char_p, dp]
+    out = np.zeros(5)
+    assert L.dfthost_settings(os.path.join(M.DATA, "molecules", "h2o_sto3g.in").encode(), out.ctypes.data_as(dp)) == 0
+    assert out.tolist() == [1.0, 0.0, 0.0, 5.0, 15.0]  # one GPU, device SCF, no dump, the reference's build_grid(5.0, 15)
+    f = tmp_path / "x.in"
+    f.write_text("gpus = 4\nscf = host\nfock = separate\ndensity_dump = data.dat\ndensity_dump_size = 7.5\ndensity_dump_points = 21\nsystem:\n")
+    assert L.dfthost_settings(str(f).encode(), out.ctypes.data_as(dp)) == 0
+    assert out.tolist() == [4.0, 2.0, 1.0, 7.5, 21.0]
+    f.write_text("density_dump_size = -1\nsystem:\n")
+    assert L.dfthost_settings(str(f).encode(), out.ctypes.data_as(dp)) < 0 and b"density_dump_size" in L.dfthost_last_error()
+    f.write_text("density_dump_points = 1\nsystem:\n")  # ignored like any other non-usable unsigned override
+    assert L.dfthost_settings(str(f).encode(), out.ctypes.data_as(dp)) == 0 and out[4] == 15.0
+
+
 def test_host_eigensolver_against_numpy():
     L, dp = _hostlib()
     rng = np.random.default_rng(3)
