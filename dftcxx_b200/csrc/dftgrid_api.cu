@@ -23,6 +23,7 @@
 #include "kernels_dense.cuh"
 #include "kernels_grid.cuh"
 #include "kernels_hartree.cuh"
+#include "kernels_integrals.cuh"
 #include "kernels_peer.cuh"
 #include "kernels_rect.cuh"
 #include "kernels_scf.cuh"
@@ -2202,6 +2203,30 @@ int dftgrid_get_amplitudes(dftgrid_t* h, double* phi) {
         CK(cudaStreamSynchronize(h->stream));
     });
 }
+// DFT::construct_matrices' integral loop (src/dft.cpp:185-198): S, T, V over the handle's basis and nuclei
+int dftgrid_one_electron(dftgrid_t* h, double* S, double* T, double* V) {
+    if (h->group) return dftgrid_one_electron(h->group->subs[0], S, T, V);
+    return guarded([&] {
+        use_device(h);
+        if (!h->built) throw std::runtime_error("dftgrid_build must be called before dftgrid_one_electron");
+        const size_t nb2 = (size_t)h->nbf * h->nbf;
+        DevBuf<double> dZ, dS;
+        std::vector<double> zq(h->Z.begin(), h->Z.end());
+        dZ.upload(zq, h->stream);
+        dS.alloc(3 * nb2);
+        const long npair = (long)h->nbf * (h->nbf + 1) / 2;
+        k_one_electron<<<(unsigned)((npair + kIntWarps - 1) / kIntWarps), kIntWarps * 32, 0, h->stream>>>(
+            h->nbf, h->natoms, h->d_bf_center.p, h->d_bf_prim_off.p, h->d_center_xyz.p, h->d_prim_exp.p, h->d_exp_alpha.p, h->d_prim_coeff.p,
+            h->d_prim_norm.p, h->d_prim_lmn.p, h->d_atom_xyz.p, dZ.p, dS.p, dS.p + nb2, dS.p + 2 * nb2);
+        h->launches++;
+        CK(cudaGetLastError());
+        if (S) CK(cudaMemcpyAsync(S, dS.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (T) CK(cudaMemcpyAsync(T, dS.p + nb2, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (V) CK(cudaMemcpyAsync(V, dS.p + 2 * nb2, nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    });
+}
+
 // RectangularGrid::build_grid + set_density (src/rectangulargrid.cpp:34-80): density and density gradient on a dp^3 box
 static void launch_rect(dftgrid* h, int PT, const double* dP, double size, int dp, long npts, double* dpos, double* drho, double* dgrad) {
     const size_t smem = (size_t)4 * PT * h->nbf * sizeof(double);

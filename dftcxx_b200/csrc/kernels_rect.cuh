@@ -39,9 +39,10 @@ k_rect_density(int nbf, const int* __restrict__ bf_center, const int* __restrict
     if (tid < PT) {
         const long p = p0 + tid;
         const long k = p % dp, j = (p / dp) % dp, i = p / ((long)dp * dp);
-        pxyz[tid][0] = (double)k * gd - size / 2.0;
-        pxyz[tid][1] = (double)j * gd - size / 2.0;
-        pxyz[tid][2] = (double)i * gd - size / 2.0;
+        // separately rounded product and difference, like the reference's C++ (no FMA contraction): bit-identical points
+        pxyz[tid][0] = __dsub_rn(__dmul_rn((double)k, gd), size / 2.0);
+        pxyz[tid][1] = __dsub_rn(__dmul_rn((double)j, gd), size / 2.0);
+        pxyz[tid][2] = __dsub_rn(__dmul_rn((double)i, gd), size / 2.0);
     }
     __syncthreads();
     for (int idx = tid; idx < PT * nbf; idx += kRectThreads) {

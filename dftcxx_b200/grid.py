@@ -75,6 +75,7 @@ def lib():
     L.dftgrid_iteration.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp]
     L.dftgrid_download_results.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     L.dftgrid_last_timings.argtypes = [C.c_void_p, _dp, C.c_int]
+    L.dftgrid_one_electron.argtypes = [C.c_void_p, _dp, _dp, _dp]
     L.dftgrid_rectangular_density.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, _dp, _dp, _dp]
     _lib = L
     return L
@@ -350,6 +351,13 @@ class MolecularGrid:
 
     def get_U_lm(self):
         return self._vec(lib().dftgrid_get_U_lm, (self.natoms, self.radial_points, self.nlm))
+
+    def one_electron(self):
+        """Overlap, kinetic-energy and nuclear-attraction matrices of the handle's basis (DFT::construct_matrices,
+        src/dft.cpp:185-198) from the device."""
+        S, T, V = (np.zeros((self.nbf, self.nbf)) for _ in range(3))
+        self._ck(lib().dftgrid_one_electron(self.h, _ptr(S), _ptr(T), _ptr(V)))
+        return S, T, V
 
     def rectangular_density(self, size, dp, P):
         """RectangularGrid::build_grid(size, dp) + set_density(P) (src/rectangulargrid.cpp:34-80): positions [dp^3][3], density

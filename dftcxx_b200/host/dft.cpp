@@ -61,16 +61,20 @@ void DFT::construct_matrices() {
         // P and F_grid cross PCIe every iteration: page-lock them once so the engine DMAs in place
         pinned = dftgrid_host_register(P.data(), sizeof(double) * n * n) == 0 && dftgrid_host_register(Fg.data(), sizeof(double) * n * n) == 0;
     }
+    if (settings->get_integrals_on_device()) {
+        molgrid->one_electron(S, T, V);  // one kernel over the upper triangle (csrc/kernels_integrals.cuh)
+    } else {
 #pragma omp parallel for schedule(dynamic)
-    for (unsigned int i = 0; i < n; i++)
-        for (unsigned int j = i; j < n; j++) {
-            S(i, j) = S(j, i) = integrator.overlap((*cgfs)[i], (*cgfs)[j]);
-            T(i, j) = T(j, i) = integrator.kinetic((*cgfs)[i], (*cgfs)[j]);
-            double v = 0.0;
-            for (unsigned int k = 0; k < mol->get_nr_atoms(); k++)
-                v += integrator.nuclear((*cgfs)[i], (*cgfs)[j], mol->get_atomic_position(k), mol->get_atomic_charge(k));
-            V(i, j) = V(j, i) = v;
-        }
+        for (unsigned int i = 0; i < n; i++)
+            for (unsigned int j = i; j < n; j++) {
+                S(i, j) = S(j, i) = integrator.overlap((*cgfs)[i], (*cgfs)[j]);
+                T(i, j) = T(j, i) = integrator.kinetic((*cgfs)[i], (*cgfs)[j]);
+                double v = 0.0;
+                for (unsigned int k = 0; k < mol->get_nr_atoms(); k++)
+                    v += integrator.nuclear((*cgfs)[i], (*cgfs)[j], mol->get_atomic_position(k), mol->get_atomic_charge(k));
+                V(i, j) = V(j, i) = v;
+            }
+    }
     H = Mat(n, n);
     for (unsigned int i = 0; i < n; i++)
         for (unsigned int j = 0; j < n; j++) H(i, j) = T(i, j) + V(i, j);

@@ -127,6 +127,14 @@ Mat MolecularGrid::scf_matrix(int which) const {
     return M;
 }
 
+void MolecularGrid::one_electron(Mat& S, Mat& T, Mat& V) {
+    const size_t n = mol->get_nr_bfs();
+    S = Mat(n, n);
+    T = Mat(n, n);
+    V = Mat(n, n);
+    check(dftgrid_one_electron(handle, S.data(), T.data(), V.data()));
+}
+
 void MolecularGrid::rectangular_density(double size, unsigned int dp, const Mat& P, double* pos, double* rho, double* grad) {
     check(dftgrid_rectangular_density(handle, size, (int)dp, P.data(), pos, rho, grad));
 }

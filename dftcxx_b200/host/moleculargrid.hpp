@@ -34,6 +34,8 @@ public:
     void scf_step(bool include_xc, double out8[8]);
     Mat scf_matrix(int which) const;  // DFTGRID_SCF_P / DFTGRID_SCF_FGRID / ... (include/dftgrid.h)
     int gpus() const;
+    // S, T, V of DFT::construct_matrices on the device (dftgrid_one_electron)
+    void one_electron(Mat& S, Mat& T, Mat& V);
     // density and density gradient on the reference's RectangularGrid box (dftgrid_rectangular_density)
     void rectangular_density(double size, unsigned int dp, const Mat& P, double* pos, double* rho, double* grad);
 

@@ -106,6 +106,7 @@ void Settings::set_default_settings() {
     if (has("lebedev_order") && parse_uint(get_value("lebedev_order"), v)) lebedev_order = v;
     if (has("lmax") && parse_uint(get_value("lmax"), v)) lmax = v;
     if (has("gpus") && parse_uint(get_value("gpus"), v) && v >= 1) gpus = v;
+    integrals_device = !(has("integrals") && get_value("integrals") == "host");
     if (has("density_dump_points") && parse_uint(get_value("density_dump_points"), v) && v >= 2) dump_points = v;
     if (has("density_dump_size")) {
         const double sz = parse_double(get_value("density_dump_size"));

@@ -29,6 +29,8 @@ public:
     unsigned int get_gpus() const { return gpus; }
     enum { SCF_DEVICE, SCF_HOST_FUSED, SCF_HOST_SEPARATE };
     unsigned int get_scf_mode() const { return scf_mode; }
+    // `integrals = device|host`: where S, T, V of DFT::construct_matrices are evaluated (default device)
+    bool get_integrals_on_device() const { return integrals_device; }
     // density dump of DFT::finalize (src/dft.cpp:489-504): `density_dump = <file>` switches it on; the two arguments of
     // RectangularGrid::build_grid default to the reference's own 5.0 / 15 (`density_dump_size`, `density_dump_points`)
     double get_density_dump_size() const { return dump_size; }
@@ -44,6 +46,7 @@ private:
     unsigned int radial_points = 15, lebedev_order = 7, lmax = 8;
     unsigned int hartree_evaluation = BECKE_GRID;
     unsigned int gpus = 1, scf_mode = SCF_DEVICE;
+    bool integrals_device = true;
     double dump_size = 5.0;
     unsigned int dump_points = 15;
 };

@@ -180,6 +180,13 @@ int dftgrid_get_potential(dftgrid_t* h, double* V /* [nloc] Hartree potential */
 int dftgrid_get_rho_lm(dftgrid_t* h, double* rho_lm /* [natoms][nrad][nlm] */);
 int dftgrid_get_U_lm(dftgrid_t* h, double* U_lm /* [natoms][nrad][nlm] */);
 
+/* The one-electron integrals of DFT::construct_matrices (src/dft.cpp:185-198; Integrator::overlap / kinetic / nuclear,
+ * src/integrals.cpp:43-387) over the handle's basis and nuclei: overlap S, kinetic energy T and nuclear attraction V
+ * (summed over all nuclei with their charges), nb x nb each, symmetric.  McMurchie-Davidson on the device with the
+ * reference's numerical conventions (pi = 3.14159265359 in the nuclear prefactor, Boys argument clamped at 1e-8).
+ * One-time work of a run.  Needs a built handle; any output may be NULL. */
+int dftgrid_one_electron(dftgrid_t* h, double* S, double* T, double* V);
+
 /* RectangularGrid::build_grid(size, dp) + set_density(P) (src/rectangulargrid.cpp:34-80) — the data DFT::finalize's density
  * dump writes (src/dft.cpp:489-504, commented out in the reference "needs to be connected to interface"): dp^3 points,
  * point (i, j, k) at index (i*dp + j)*dp + k and position ((k, j, i) * size/(dp-1) - size/2) in the molecule's frame,
