@@ -798,6 +798,16 @@ void do_build(dftgrid* h) {
     g.npts = (long)g.natoms * g.nrad * g.nang;
     const long nshell = (long)g.natoms * g.nrad;
     h->leb_off = lebedev_offset(prm.lebedev_order);
+    // developer instrumentation (DFTGRID_DEBUG_BUILD_TIMES): wall clock of the build's host-side milestones
+    static const bool build_times = std::getenv("DFTGRID_DEBUG_BUILD_TIMES") != nullptr;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!build_times) return;
+        CK(cudaStreamSynchronize(st));
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[dftgrid] build rank %d: %-28s %8.1f ms\n", h->rank, what, std::chrono::duration<double, std::milli>(now - t_mark).count());
+        t_mark = now;
+    };
 
     // ---- host tables
     std::vector<double> r, wr, Y, pre;
@@ -825,6 +835,7 @@ void do_build(dftgrid* h) {
             Rdist[(size_t)a * g.natoms + b] = std::sqrt(dx * dx + dy * dy + dz * dz);
         }
 
+    mark("host tables");
     h->d_atom_xyz.upload(h->atom_xyz, st);
     h->d_Rdist.upload(Rdist, st);
     h->d_rtab.upload(r, st);
@@ -862,6 +873,7 @@ void do_build(dftgrid* h) {
     h->d_prim_exp.upload(h->prim_exp, st);
     h->d_prim_lmn.upload(h->prim_lmn, st);
 
+    mark("table uploads");
     // ---- per-point storage
     const size_t nl = (size_t)g.nloc, nlp = nl + 64;
     h->d_x.alloc(nlp);
@@ -917,6 +929,7 @@ void do_build(dftgrid* h) {
     if (becke_smem > 200 * 1024) throw std::runtime_error("too many atoms for the Becke kernel's shared-memory layout");
     CK(cudaFuncSetAttribute(k_becke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(becke_smem, 1024)));
 
+    mark("allocations + attributes");
     // ---- kernels
     record(h, 0);
     if (g.nloc > 0) {
@@ -1012,8 +1025,11 @@ void do_build(dftgrid* h) {
         h->launches++;
     }
     record(h, 3);
+    mark("points, Becke, Phi");
     build_active_lists(h, nsm);
+    mark("block map, schedule, calibration");
     build_pair_bins(h);
+    mark("interpolation pair bins");
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     h->t_ms[DFTGRID_T_POINTS] = elapsed(h, 0, 1);

@@ -61,6 +61,8 @@ void DFT::construct_matrices() {
         // P and F_grid cross PCIe every iteration: page-lock them once so the engine DMAs in place
         pinned = dftgrid_host_register(P.data(), sizeof(double) * n * n) == 0 && dftgrid_host_register(Fg.data(), sizeof(double) * n * n) == 0;
     }
+    const bool timings = verbose && std::getenv("DFTCXX_TIMINGS");
+    auto t_phase = clk::now();
     if (settings->get_integrals_on_device()) {
         molgrid->one_electron(S, T, V);  // one kernel over the upper triangle (csrc/kernels_integrals.cuh)
     } else {
@@ -75,11 +77,14 @@ void DFT::construct_matrices() {
                 V(i, j) = V(j, i) = v;
             }
     }
+    if (timings) std::printf("\tone-electron integrals (%s): %.1f ms\n", settings->get_integrals_on_device() ? "device" : "host", ms_since(t_phase));
     H = Mat(n, n);
     for (unsigned int i = 0; i < n; i++)
         for (unsigned int j = 0; j < n; j++) H(i, j) = T(i, j) + V(i, j);
     calculate_nuclear_repulsion();
+    t_phase = clk::now();
     calculate_transformation_matrix();
+    if (timings) std::printf("\torthogonalisation X = U s^-1/2 (host eigen-solver): %.1f ms\n", ms_since(t_phase));
     if (scf_mode == Settings::SCF_DEVICE) {
         // H and X go to the device once; from here on P, F and the whole SCF algebra live in HBM
         molgrid->scf_init(H, X, nelec / 2, 0.50);

@@ -106,6 +106,8 @@ def test_memcheck_clean_on_a_small_iteration():
         "nocc = int(round(float(g['nel']))) // 2\n"
         "mg.scf_init(g['scf_H'], g['scf_X'], nocc, 0.5); mg.scf_step(False); mg.scf_step(True)\n"
         "assert np.max(np.abs(J - g['J'])) < 1e-10 and np.max(np.abs(F - 2 * g['J'] - g['XC'])) < 3e-10\n"
+        "S, T, V = mg.one_electron(); assert np.max(np.abs(S - g['scf_S'])) < 1e-13 and np.max(np.abs(T + V - g['scf_H'])) < 1e-11\n"
+        "pos, rho, grad = mg.rectangular_density(5.0, 6, g['P']); assert np.isfinite(grad).all() and rho.min() >= 0.0\n"
         "mg.close(); print('SANITIZED_RUN_OK')\n" % (ROOT, os.path.join(ROOT, "tests")))
     r = subprocess.run([exe, "--tool", "memcheck", "--error-exitcode", "9", sys.executable, "-c", code], capture_output=True, text=True,
                        timeout=900, cwd=ROOT)
