@@ -119,7 +119,10 @@ def reference_fit(workload, mol, prm, threads, whole=False):
         rho + XC phase ~ b * Npts*nb^2             (src/gridpoint.cpp:82-84, src/dft.cpp:424-432)
     and evaluated at the full size; the relative residuals of the fit at the three sizes are reported.  The nb^2 J assembly
     hidden inside the Hartree phase is NOT scaled up, so the extrapolation is a lower bound of the reference's time.  Note
-    that the nb^2 terms of oracle/_ref run on the header shim's plain loops, not on a real Eigen (the image has none).
+    that the nb^2 terms of oracle/_ref run on the header shim (the image has no Eigen).  The shim serves rows of large column-major
+    matrices from a row-major mirror, so the reference's nb^2 strided dot products (src/dft.cpp:424-432,
+    src/atomicgrid.cpp:479-487) read contiguous memory — a real Eigen build walks them with stride nb and is SLOWER; the CPU
+    figure is therefore on the fast side, the GPU/CPU ratio on the conservative side.
     Returns (ms, description, details)."""
     from oracle import refpy
 
@@ -172,7 +175,8 @@ def reference_fit(workload, mol, prm, threads, whole=False):
     desc = ("bounded sample: sub-clusters of the same geometry with %s molecules (%s s of CPU per iteration, measured); per-phase times "
             "least-squares fitted to the reference's loop bounds (Hartree ~ Npts*(Natoms-1)*nlm, rho+XC ~ Npts*nb^2), fit residuals %s; "
             "evaluated at the full workload: EXTRAPOLATED lower bound (single-sample extrapolations: %s s); the nb^2 terms run on the "
-            "header shim's plain loops, not on Eigen" % ("/".join(str(x) for x in sizes), "/".join("%.1f" % (t / 1e3) for t in ts),
+            "header shim, whose row-major mirror makes the reference's strided nb^2 dot products contiguous (a real Eigen build is slower there: "
+            "the CPU figure errs on the fast side)" % ("/".join(str(x) for x in sizes), "/".join("%.1f" % (t / 1e3) for t in ts),
                                                          "/".join("%+.1f%%" % (100 * r) for r in resid), "/".join("%.0f" % (v / 1e3) for v in lo_hi)))
     return float(full), desc, {"extrapolated": True, "measured_s": [t / 1e3 for t in ts], "sample_molecules": list(sizes), "a_ms": a, "b_ms": b,
                                "fit_residuals": resid, "single_sample_extrapolations_ms": lo_hi}
