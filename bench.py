@@ -450,9 +450,12 @@ def main():
             "second_kernel": {"kernel": "k_rho_tma", "ms": rho_ms, "achieved_full_2Nnb2": 2.0 * npts_loc * mol.nbf ** 2 / (rho_ms * 1e-3) / 1e12 if rho_ms > 0 else None,
                               "note": "executes half of 2*Npts*nb^2 (P symmetric): frac of peak on executed flops = achieved/2/peak"}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and ngpus_total == 1:  # the capture is of the whole grid on one GPU; a shard's launch reads its own rows only
         try:
-            roof["traffic"] = json.load(open(prof)).get(args.workload, {}).get("k_contract_fock_dram_bytes")
+            tj = json.load(open(prof)).get(args.workload, {})
+            roof["traffic"] = tj.get("k_contract_fock_dram_bytes")
+            roof["traffic_algorithmic"] = tj.get("k_contract_fock_algorithmic_bytes")
+            roof["traffic_source"] = tj.get("source_r02b") or tj.get("source_r02") or tj.get("source")
         except Exception:
             pass
 
