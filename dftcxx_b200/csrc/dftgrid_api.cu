@@ -136,8 +136,10 @@ struct dftgrid {
     struct DevSchedule {
         DevBuf<ConSeg> segs;
         DevBuf<int> cta_off, item_off;
-        int ctas = 1, nsegs = 1;
+        int ctas = 1, nsegs = 1, n_single = 0;  // n_single: CTAs with exactly one segment (the ones that keep the soft lockstep)
     } sched[2];
+    DevBuf<unsigned> d_con_sync;  // window counters of the contraction's soft lockstep (kernels_dense.cuh: ConSync)
+    int con_sync_wc = 0, con_sync_lead = 2, con_sync_pct = 100;
     DevBuf<double> d_fres;  // fused build: [F (nb^2) | per-shell sums of w V rho (natoms*nrad) | e_j, exc, nel, pad]
     DevBuf<double> d_rho_part;  // partial densities when a tile's slabs are split over several CTAs
     int rho_split = 1;
@@ -424,6 +426,8 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector
         dftgrid::DevSchedule& D = h->sched[k];
         D.ctas = (int)S.cta_off.size() - 1;
         D.nsegs = (int)S.segs.size();
+        D.n_single = 0;
+        for (int c = 0; c < D.ctas; c++) D.n_single += S.cta_off[c + 1] - S.cta_off[c] == 1 ? 1 : 0;
         D.segs.alloc(S.segs.size());
         CK(cudaMemcpyAsync(D.segs.p, S.segs.data(), S.segs.size() * sizeof(ConSeg), cudaMemcpyHostToDevice, st));
         D.cta_off.upload(S.cta_off, st);
@@ -440,6 +444,26 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector
         CK(cudaStreamSynchronize(st));  // S goes out of scope
     }
     h->d_partial.alloc(max_segs * kTileM * kTileN);
+    {
+        // soft lockstep of the sweep (kernels_dense.cuh: ConSync): windows of 24 MB of Phi rows, at most 2 windows of lead
+        // (developer switches DFTGRID_CON_SYNC_MB, 0 = off, _LEAD, _PCT); only when the sweep has enough windows.  Measured at
+        // (H2O)64 on the calibrated shares: DRAM reads 7.0 -> 4.7 GB per launch (1.26x the algorithmic 3.73 GB), 8.73 -> 8.62 ms
+        static const char* mb = std::getenv("DFTGRID_CON_SYNC_MB");
+        static const char* lead = std::getenv("DFTGRID_CON_SYNC_LEAD");
+        static const char* pct = std::getenv("DFTGRID_CON_SYNC_PCT");
+        const double sync_mb = mb ? std::atof(mb) : 24.0;
+        const double chunk_bytes = (double)kTileK * h->nbp * sizeof(double);
+        h->con_sync_wc = 0;
+        if (sync_mb > 0.0) {
+            const long wc = std::max<long>(32, (long)(sync_mb * 1e6 / chunk_bytes));
+            if (nchunk >= 8 * wc) {
+                h->con_sync_wc = (int)wc;
+                h->con_sync_lead = lead ? std::max(1, std::atoi(lead)) : 2;
+                h->con_sync_pct = pct ? std::min(100, std::max(1, std::atoi(pct))) : 100;
+                h->d_con_sync.alloc((size_t)((nchunk + wc - 1) / wc) + 1);
+            }
+        }
+    }
 }
 
 // Measured cost model of the screened contraction.  The analytic weights (DMMA counts per tile kind x the map's work
@@ -514,19 +538,22 @@ void calibrate_contract_costs(dftgrid* h, int nsm, const std::vector<double>& si
                              per_stage[p], samples[p].size(), sig_frac[p]);
         return pair_cost;
     };
-    // Autotuning loop: the analytic schedule, then up to two schedules cut on what the previous one measured; the fastest
-    // measured schedule is kept (a re-cut is not always a gain: the CTAs at item boundaries and their SM-pair neighbours
-    // carry overheads that are not a property of the pair).
+    // Autotuning loop: the analytic schedule, then up to three schedules cut on what the previous one measured.  The fastest
+    // measured-cost schedule is kept unless it is more than 1 % SLOWER than the analytic one: at equal speed the measured
+    // costs are still the better choice, because CTAs whose shares match their real pace sweep the Phi rows in step and
+    // share them through the L2 (ncu at (H2O)64: 7.0 GB of DRAM reads per launch, L2 hit rate 53 %, against 13.1 GB / 28 %
+    // for the analytic shares at 8.4 vs 8.6 ms — profiles/r02b_contract_dram_per_launch.txt).
     std::vector<double> us, stages, best_cost, cur_cost;
-    double best = measure(us, stages);
-    if (verbose) std::fprintf(stderr, "[dftgrid] contraction schedule, analytic costs: %.1f us\n", best);
-    for (int round = 0; round < 2; round++) {
+    const double t_analytic = measure(us, stages);
+    double best = 1.01 * t_analytic;
+    if (verbose) std::fprintf(stderr, "[dftgrid] contraction schedule, analytic costs: %.1f us\n", t_analytic);
+    for (int round = 0; round < 3; round++) {
         cur_cost = costs_from(us, stages);
         if (cur_cost.empty()) break;
         build_contract_schedule(h, h->n_active_chunks, nsm, nullptr, &cur_cost);
         const double tcur = measure(us, stages);
         if (verbose) std::fprintf(stderr, "[dftgrid] contraction schedule, measured costs (round %d): %.1f us\n", round + 1, tcur);
-        if (tcur < 0.98 * best) {
+        if (tcur < best) {
             best = tcur;
             best_cost = cur_cost;
         }
@@ -1200,9 +1227,14 @@ void run_contract(dftgrid* h, int mode) {
         h->peer_used = true;
         h->launches++;
     }
+    ConSync csync{nullptr, 1, 0, 0};
+    if (h->con_sync_wc > 0 && D.n_single >= 16) {
+        h->d_con_sync.zero(st);
+        csync = ConSync{h->d_con_sync.p, h->con_sync_wc, h->con_sync_lead, std::max(1, D.n_single * h->con_sync_pct / 100)};
+    }
     k_contract_tma<<<D.ctas, kConTmaThreads, kConTmaSmemBytes, st>>>(h->d_phi.p, fock ? h->d_dF.p : h->d_dxc.p, h->d_dJ.p,
                                                                      h->screened ? h->d_con_chunk_ids.p : h->d_chunk_ids.p,
-                                                                     h->screened ? h->d_con_chunk_mask.p : nullptr, h->d_pairs.p, D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc, h->d_dbg_times.p);
+                                                                     h->screened ? h->d_con_chunk_mask.p : nullptr, h->d_pairs.p, D.segs.p, D.cta_off.p, h->d_partial.p, h->nbp, (int)h->n_active_chunks, h->con_bc, h->d_dbg_times.p, csync);
     if (h->d_dbg_times.p && !h->capturing) {
         // developer instrumentation: per-CTA wall time of the contraction with the CTA's segments
         std::vector<unsigned long long> t(3 * (size_t)D.ctas);

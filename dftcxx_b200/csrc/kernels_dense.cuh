@@ -509,6 +509,16 @@ __device__ __forceinline__ bool con_owns(const ConSeg& sg, int x, unsigned long 
 }
 __device__ __forceinline__ unsigned long long con_tile_bits(int t) { return 0xFull << (4 * t); }
 
+// Soft lockstep of the sweep (optional): the A producer of every single-segment CTA counts the windows of `wc` chunk
+// positions it has finished in prog[] and does not enter window w before `quorum` such CTAs have finished window
+// w - lead, so the CTAs that share Phi rows through the L2 stay within lead + 1 windows of each other.  Waiting never
+// lengthens the critical path by itself (the slowest CTA never waits); the spin is bounded (~2 ms) and falls back to free
+// running, so a grid that is not fully co-resident cannot deadlock.  prog[] is zeroed before every launch.
+struct ConSync {
+    unsigned* prog;
+    int wc, lead, quorum;
+};
+
 constexpr int kConTmaThreads = kDenseThreads + 128;  // 2 DMMA warpgroups + 1 producer warpgroup: warp 8 operand A, warp 9 operand B and the weights
 constexpr size_t kConTmaSmemBytes = (size_t)kStages * kConStageDoubles * sizeof(double) + 2 * kStages * sizeof(unsigned long long);
 
@@ -769,7 +779,7 @@ __global__ void __launch_bounds__(kConTmaThreads, 1)
 k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, const double* __restrict__ d1, const int* __restrict__ chunk_ids,
                const unsigned long long* __restrict__ chunk_mask, const int* __restrict__ pair_ij, const ConSeg* __restrict__ segs,
                const int* __restrict__ cta_seg_off, double* __restrict__ partial, int nbp, int nchunk, int bc,
-               unsigned long long* __restrict__ dbg_times = nullptr) {
+               unsigned long long* __restrict__ dbg_times = nullptr, ConSync sync = ConSync{nullptr, 1, 0, 0}) {
     extern __shared__ __align__(128) double sm[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)kStages * kConStageDoubles);
     unsigned long long* empty = full + kStages;
@@ -794,6 +804,8 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
         if (warp > 9) return;
         const bool prodA = warp == 8;
+        bool throttle = prodA && sync.prog != nullptr && s_end - s_begin == 1;
+        int cur_w = 0;
         for (int b = 0; b < nblock; b++) {
             for (int sidx = s_begin; sidx < s_end; sidx++) {
                 const ConSeg sg = segs[sidx];
@@ -836,6 +848,33 @@ k_contract_tma(const double* __restrict__ phi, const double* __restrict__ d0, co
                 size_t pend_row0 = 0;
                 unsigned long long pend_cm = 0ull;
                 for (int base = x0; base < x1; base += 32) {
+                    if (throttle) {
+                        const int w = base / sync.wc;
+                        if (w != cur_w) {  // entering a new window: the earlier ones are done; wait for the pack
+                            int gave_up = 0;
+                            if (lane == 0) {
+                                for (int v = cur_w; v < w; v++) atomicAdd(sync.prog + v, 1u);
+                                if (w >= sync.lead) {
+                                    const volatile unsigned* flag = sync.prog + (w - sync.lead);
+                                    unsigned spins = 0;
+                                    while (*flag < (unsigned)sync.quorum) {
+                                        __nanosleep(100);
+                                        if (++spins > 20000u) {  // ~2 ms: give up the lockstep, never the run
+                                            gave_up = 1;
+                                            break;
+                                        }
+                                    }
+                                }
+                            }
+                            gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
+                            cur_w = w;
+                            if (gave_up) {  // keep the counts moving for the others, stop waiting
+                                throttle = false;
+                                if (lane == 0)
+                                    for (int v = w; v < (nchunk + sync.wc - 1) / sync.wc; v++) atomicAdd(sync.prog + v, 1u);
+                            }
+                        }
+                    }
                     const int x = base + lane;
                     const unsigned long long cm = (x < x1 && chunk_mask) ? chunk_mask[x] : ~0ull;
                     unsigned mask = __ballot_sync(0xffffffffu, x < x1 && con_owns(sg, x, cm, mi, mj));
