@@ -150,10 +150,11 @@ struct dftgrid {
     DevBuf<double> d_Vpart;
     // binned interpolation (see kernels_hartree.cuh): pairs sorted by (source atom, spline interval) at build time
     bool binned = false;
-    int bin_R = 2, bin_nkeys = 0;
+    int bin_R = 2, bin_nkeys = 0;  // pairs per lane of k_interp_bin (3 with the precomputed pair geometry)
     long bin_nitems = 0;
     DevBuf<int> d_binoff, d_item_key, d_pair_point, d_slot_of;
     DevBuf<double> d_pair_out;
+    DevBuf<double> d_pair_geo;  // [6][slots]: 1/r, t, cos / sin(theta), cos / sin(phi) of every pair (k_pair_geometry), when it fits
 
     // pinned staging
     double* h_P = nullptr;
@@ -698,14 +699,21 @@ void build_pair_bins(dftgrid* h) {
     if (std::getenv("DFTGRID_INTERP_POINTWISE")) return;  // developer A/B switch
     if (!(g.lmax == 5 || g.lmax == 8 || g.lmax == 10 || g.lmax == 11)) return;
     if (g.nloc == 0 || g.natoms < 2) return;
+    const int nkeys = g.natoms * g.nrad;
+    size_t mem_free = 0, mem_total = 0;
+    CK(cudaMemGetInfo(&mem_free, &mem_total));
+    // pairs per lane: 3 when the pairs' geometry can be kept (k_pair_geometry: the kernel then has the registers for a third
+    // pair per lane, measured 5.73 -> 5.48 ms at (H2O)64), 2 otherwise; DFTGRID_INTERP_R overrides (developer switch)
+    static const bool no_geo = std::getenv("DFTGRID_NO_PAIR_GEO") != nullptr;  // developer A/B switch
+    const double pairs_est = (double)g.nloc * (g.natoms - 1) + (double)nkeys * 96.0;
+    const double lists = pairs_est * 12.0 + (double)g.nloc * g.natoms * 4.0;
+    const bool want_geo = !no_geo && lists + pairs_est * 48.0 < 0.45 * (double)mem_free;
+    h->bin_R = want_geo ? 3 : 2;
     if (const char* r = std::getenv("DFTGRID_INTERP_R")) h->bin_R = std::atoi(r);
     if (h->bin_R < 2 || h->bin_R > 4) h->bin_R = 2;
     const int unit = 32 * h->bin_R;
-    const int nkeys = g.natoms * g.nrad;
     const double pairs_max = (double)g.nloc * (g.natoms - 1) + (double)nkeys * unit;
     if (pairs_max >= 2.0e9) return;
-    size_t mem_free = 0, mem_total = 0;
-    CK(cudaMemGetInfo(&mem_free, &mem_total));
     if (pairs_max * 12.0 + (double)g.nloc * g.natoms * 4.0 > 0.5 * (double)mem_free) return;
 
     DevBuf<int> d_counts, d_cursor;
@@ -739,6 +747,18 @@ void build_pair_bins(dftgrid* h) {
     if (h->bin_nitems > 0)
         k_item_keys<<<(unsigned)((h->bin_nitems + 255) / 256), 256, 0, st>>>(h->d_binoff.p, nkeys, unit, h->bin_nitems, h->d_item_key.p);
     h->launches += 3;
+    // the pairs' geometry, once (48 bytes per slot), when it fits comfortably beside what the iteration still allocates
+    h->d_pair_geo.release();
+    {
+        CK(cudaMemGetInfo(&mem_free, &mem_total));
+        const double need = 6.0 * 8.0 * (double)total;
+        if (want_geo && total > 0 && need < 0.4 * (double)mem_free) {
+            h->d_pair_geo.alloc(6 * (size_t)total);
+            k_pair_geometry<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, h->d_item_key.p,
+                                                                              h->d_pair_point.p, unit, total, h->d_pair_geo.p);
+            h->launches++;
+        }
+    }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));  // binoff (host vector) and the scratch buffers go out of scope
     h->binned = true;
@@ -777,9 +797,10 @@ void shard_shells(dftgrid* h, const std::vector<double>& rtab, long nshell, long
     // per-point cost model (ns, B200): the density kernel executes nb^2 DMMA flops per point on the significant blocks
     // (~ fsig^2), the fused contraction nb (nb + 1) of which screening removes less (masked stages have a floor, diagonal
     // tiles run whole: ~ fsig, measured on the shards of (H2O)64), the interpolation 6.2 FP64 operations per
-    // (point, source atom, lm) at ~70 % of the FP64 pipe whatever the map says
+    // (point, source atom, lm) at ~70 % of the FP64 pipe whatever the map says (5.5 ms per 1.3e10 terms with the pairs'
+    // geometry precomputed)
     const int lmax = h->prm.lmax, nlm = (lmax + 1) * (lmax + 1);
-    const double t_dense = (double)h->nbf * h->nbf / 37.0e3, t_interp = (double)(na - 1) * nlm * 6.2 / 13.0e3;
+    const double t_dense = (double)h->nbf * h->nbf / 37.0e3, t_interp = (double)(na - 1) * nlm * 6.2 / 14.7e3;
     std::vector<double> cum((size_t)nshell + 1, 0.0);
     std::vector<double> dist(h->nbf);
     for (int a = 0; a < na; a++) {
@@ -1148,18 +1169,25 @@ void run_potential(dftgrid* h) {
         if (h->bin_nitems > 0) {
             const unsigned bx = (unsigned)((h->bin_nitems + kBinWarps - 1) / kBinWarps);
             const size_t smem = (size_t)kBinWarps * g.nlm * 4 * sizeof(double);
-#define DFG_BIN_ARGS g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, h->d_coef.p, h->d_item_key.p, h->d_pair_point.p, h->bin_nitems, h->d_pair_out.p
+#define DFG_BIN_ARGS g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, h->d_coef.p, h->d_item_key.p, h->d_pair_point.p, h->bin_nitems, h->d_pair_out.p, h->d_pair_geo.p, (long)h->bin_nitems * 32 * h->bin_R
+#define DFG_BIN_LAUNCH(LL, RR, MB)                                                                              \
+    if (geo)                                                                                                    \
+        k_interp_bin<LL, RR, MB, true><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                         \
+    else                                                                                                        \
+        k_interp_bin<LL, RR, MB, false><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS)
 #define DFG_BIN_CASE(LL)                                                                                        \
     case LL:                                                                                                    \
-        if (h->bin_R == 4)                                                                                      \
-            k_interp_bin<LL, 4, 3><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                            \
-        else if (h->bin_R == 3)                                                                                 \
-            k_interp_bin<LL, 3, 4><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                            \
-        else if (five)                                                                                          \
-            k_interp_bin<LL, 2, 5><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                            \
-        else                                                                                                    \
-            k_interp_bin<LL, 2, 6><<<bx, kBinWarps * 32, smem, st>>>(DFG_BIN_ARGS);                            \
+        if (h->bin_R == 4) {                                                                                    \
+            DFG_BIN_LAUNCH(LL, 4, 3);                                                                           \
+        } else if (h->bin_R == 3) {                                                                             \
+            DFG_BIN_LAUNCH(LL, 3, 4);                                                                           \
+        } else if (five) {                                                                                      \
+            DFG_BIN_LAUNCH(LL, 2, 5);                                                                           \
+        } else {                                                                                                \
+            DFG_BIN_LAUNCH(LL, 2, 6);                                                                           \
+        }                                                                                                       \
         break;
+            const bool geo = h->d_pair_geo.p != nullptr;
             static const bool five = std::getenv("DFTGRID_INTERP_MINB5") != nullptr;  // developer A/B switch
             switch (g.lmax) {
                 DFG_BIN_CASE(5)
@@ -1169,6 +1197,7 @@ void run_potential(dftgrid* h) {
                 default: throw std::runtime_error("binned interpolation: unsupported lmax");
             }
 #undef DFG_BIN_CASE
+#undef DFG_BIN_LAUNCH
 #undef DFG_BIN_ARGS
             h->launches++;
         }

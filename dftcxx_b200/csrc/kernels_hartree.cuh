@@ -633,16 +633,68 @@ __device__ __forceinline__ void static_for(F&& f) {
     }
 }
 
+// Geometry of one (point, source atom) pair as the interpolation consumes it: 1/r, the spline abscissa t = r - x_row
+// (0 below the first node: the spline is clamped to y.front()), cos / sin(theta), cos / sin(phi).
+struct PairGeo {
+    double rinv, tt, ct, st, c1, s1;
+};
+__device__ __forceinline__ PairGeo pair_geometry(double dx, double dy, double dz, double x_first, double x_row) {
+    PairGeo q;
+    const double r = pair_dist(dx, dy, dz);
+    q.rinv = 1.0 / r;
+    q.tt = r < x_first ? 0.0 : r - x_row;
+    q.ct = dz / r;  // cos(theta) = z/r by true division: exactly +-1 on the axis, like cos(acos(z/r))
+    q.st = sqrt(1.0 - q.ct * q.ct);
+    const double rxy = sqrt(dx * dx + dy * dy);
+    q.c1 = 1.0;
+    q.s1 = 0.0;  // atan2(0,0) = 0
+    if (rxy > 0.0) {
+        const double ri = 1.0 / rxy;
+        q.c1 = dx * ri;
+        q.s1 = dy * ri;
+    }
+    return q;
+}
+
+// The pairs never move during an SCF (points and nuclei are fixed), so their geometry is evaluated ONCE at grid build, in
+// bin order, as six SoA arrays geo[q][slot] (48 bytes per pair: 5.1 GB at (H2O)64).  k_interp_bin<.., GEO = true> then starts
+// from six coalesced loads instead of a dependent gather (slot -> point -> x, y, z) followed by two square roots and three
+// divisions per pair: that prologue held 30 % of the kernel's stall samples (profiles/r02c_ncu_hot_h2o64.txt).  Pad slots
+// get the same harmless dummy the kernel used to build for them.
+__global__ void k_pair_geometry(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ px, const double* __restrict__ py,
+                                const double* __restrict__ pz, const double* __restrict__ xs, const int* __restrict__ item_key,
+                                const int* __restrict__ pair_point, int unit, long nslots, double* __restrict__ geo) {
+    const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    const int key = item_key[slot / unit];
+    const int N = g.nrad, k = key / N, row = key - k * N;
+    const int p = pair_point[slot];
+    double dx = 1.0, dy = 1.0, dz = 1.0;
+    if (p >= 0) {
+        dx = px[p] - atom_xyz[3 * k];
+        dy = py[p] - atom_xyz[3 * k + 1];
+        dz = pz[p] - atom_xyz[3 * k + 2];
+    }
+    const PairGeo q = pair_geometry(dx, dy, dz, xs[0], xs[row]);
+    geo[slot] = q.rinv;
+    geo[nslots + slot] = q.tt;
+    geo[2 * nslots + slot] = q.ct;
+    geo[3 * nslots + slot] = q.st;
+    geo[4 * nslots + slot] = q.c1;
+    geo[5 * nslots + slot] = q.s1;
+}
+
 constexpr int kBinWarps = 4;  // warps (= work items) per CTA of the binned kernel
 
 // One warp per item = 32*R consecutive slots of one bin (bins are padded to a multiple of 32*R; pad slots hold -1).
 // Arithmetic per pair: Legendre columns by the reference's recurrences (src/spherical_harmonics.cpp:81-117),
 // cos/sin(m phi) by angle addition, cubic in Horner form; 1/r is applied once to the pair's sum.
-template <int L, int R, int MINB>
+template <int L, int R, int MINB, bool GEO = false>
 __global__ void __launch_bounds__(kBinWarps * 32, MINB)
 k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __restrict__ px, const double* __restrict__ py,
              const double* __restrict__ pz, const double* __restrict__ xs, const double* __restrict__ coef,
-             const int* __restrict__ item_key, const int* __restrict__ pair_point, long nitems, double* __restrict__ out) {
+             const int* __restrict__ item_key, const int* __restrict__ pair_point, long nitems, double* __restrict__ out,
+             const double* __restrict__ geo = nullptr, long nslots = 0) {
     constexpr int NLM = (L + 1) * (L + 1);
     extern __shared__ __align__(128) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -667,37 +719,50 @@ k_interp_bin(GridShape g, const double* __restrict__ atom_xyz, const double* __r
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    const double ax = atom_xyz[3 * k], ay = atom_xyz[3 * k + 1], az = atom_xyz[3 * k + 2];
-    const double x_first = xs[0], x_row = xs[row];
     double tt[R], ct[R], st[R], c1[R], s1[R], rinv[R], cm[R], sn[R], pmm[R], acc[R];
     bool live[R];
+    if constexpr (GEO) {
+        (void)row;
 #pragma unroll
-    for (int j = 0; j < R; j++) {
-        const int p = pidx[j];
-        live[j] = p >= 0;
-        double dx = 1.0, dy = 1.0, dz = 1.0;  // pad lanes evaluate a harmless dummy
-        if (live[j]) {
-            dx = px[p] - ax;
-            dy = py[p] - ay;
-            dz = pz[p] - az;
+        for (int j = 0; j < R; j++) {
+            const long s = slot0 + j * 32 + lane;
+            live[j] = true;  // pad slots hold the dummy geometry and own a result slot nobody reads
+            rinv[j] = geo[s];
+            tt[j] = geo[nslots + s];
+            ct[j] = geo[2 * nslots + s];
+            st[j] = geo[3 * nslots + s];
+            c1[j] = geo[4 * nslots + s];
+            s1[j] = geo[5 * nslots + s];
+            cm[j] = 1.0;
+            sn[j] = 0.0;
+            pmm[j] = 1.0;
+            acc[j] = 0.0;
         }
-        const double r = pair_dist(dx, dy, dz);
-        rinv[j] = 1.0 / r;
-        tt[j] = r < x_first ? 0.0 : r - x_row;  // below the first node the spline is clamped to y.front()
-        ct[j] = dz / r;  // cos(theta) = z/r by true division: exactly +-1 on the axis, like cos(acos(z/r))
-        st[j] = sqrt(1.0 - ct[j] * ct[j]);
-        const double rxy = sqrt(dx * dx + dy * dy);
-        c1[j] = 1.0;
-        s1[j] = 0.0;  // atan2(0,0) = 0
-        if (rxy > 0.0) {
-            const double ri = 1.0 / rxy;
-            c1[j] = dx * ri;
-            s1[j] = dy * ri;
+    } else {
+        const double ax = atom_xyz[3 * k], ay = atom_xyz[3 * k + 1], az = atom_xyz[3 * k + 2];
+        const double x_first = xs[0], x_row = xs[row];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const int p = pidx[j];
+            live[j] = p >= 0;
+            double dx = 1.0, dy = 1.0, dz = 1.0;  // pad lanes evaluate a harmless dummy
+            if (live[j]) {
+                dx = px[p] - ax;
+                dy = py[p] - ay;
+                dz = pz[p] - az;
+            }
+            const PairGeo q = pair_geometry(dx, dy, dz, x_first, x_row);
+            rinv[j] = q.rinv;
+            tt[j] = q.tt;
+            ct[j] = q.ct;
+            st[j] = q.st;
+            c1[j] = q.c1;
+            s1[j] = q.s1;
+            cm[j] = 1.0;
+            sn[j] = 0.0;
+            pmm[j] = 1.0;
+            acc[j] = 0.0;
         }
-        cm[j] = 1.0;
-        sn[j] = 0.0;
-        pmm[j] = 1.0;
-        acc[j] = 0.0;
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncwarp();
