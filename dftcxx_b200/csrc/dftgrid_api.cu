@@ -707,7 +707,7 @@ void build_pair_bins(dftgrid* h) {
     static const bool no_geo = std::getenv("DFTGRID_NO_PAIR_GEO") != nullptr;  // developer A/B switch
     const double pairs_est = (double)g.nloc * (g.natoms - 1) + (double)nkeys * 96.0;
     const double lists = pairs_est * 12.0 + (double)g.nloc * g.natoms * 4.0;
-    const bool want_geo = !no_geo && lists + pairs_est * 48.0 < 0.45 * (double)mem_free;
+    const bool want_geo = !no_geo && lists + pairs_est * 48.0 < 0.8 * (double)mem_free;  // nothing large is allocated after this
     h->bin_R = want_geo ? 3 : 2;
     if (const char* r = std::getenv("DFTGRID_INTERP_R")) h->bin_R = std::atoi(r);
     if (h->bin_R < 2 || h->bin_R > 4) h->bin_R = 2;
@@ -752,7 +752,7 @@ void build_pair_bins(dftgrid* h) {
     {
         CK(cudaMemGetInfo(&mem_free, &mem_total));
         const double need = 6.0 * 8.0 * (double)total;
-        if (want_geo && total > 0 && need < 0.4 * (double)mem_free) {
+        if (want_geo && total > 0 && need < 0.85 * (double)mem_free) {
             h->d_pair_geo.alloc(6 * (size_t)total);
             k_pair_geometry<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, h->d_atom_xyz.p, h->d_x.p, h->d_y.p, h->d_z.p, h->d_xs.p, h->d_item_key.p,
                                                                               h->d_pair_point.p, unit, total, h->d_pair_geo.p);
