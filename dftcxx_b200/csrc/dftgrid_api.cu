@@ -1499,7 +1499,7 @@ template <bool SYM>
 void scf_gemm(dftgrid* h, const double* A, const double* B, double* C, const int* skip) {
     const int np = h->scf.np, nt = np / kGemmTile;
     if (SYM)
-        k_gemm_nn<true><<<nt * (nt + 1) / 2, kGemmThreads, kGemmSmemBytes, h->stream>>>(A, B, C, np, skip);
+        k_gemm_sym32<<<nt * (nt + 1), kGemmThreads, kGemmSmemBytes2, h->stream>>>(A, B, C, np, skip);  // sum over ti of 2 (nt - ti) half-width tiles
     else
         k_gemm_nn<false><<<dim3(nt, nt), kGemmThreads, kGemmSmemBytes, h->stream>>>(A, B, C, np, skip);
     h->launches++;
@@ -1526,6 +1526,7 @@ void scf_init(dftgrid* h, const double* H, const double* X, int nocc, double alp
     for (auto& e : S.ev)
         if (!e) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_gemm_nn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(k_gemm_sym32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes2));
     CK(cudaFuncSetAttribute(k_gemm_nn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
     // H and X arrive row-major nb x nb (H symmetric; X = U s^-1/2 is not): pad X, build X^T once
     CK(cudaMemcpyAsync(S.H.p, H, nb2 * sizeof(double), cudaMemcpyHostToDevice, st));

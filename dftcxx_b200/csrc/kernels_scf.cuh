@@ -138,6 +138,99 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_nn(const double* __restri
         }
 }
 
+// Symmetric product on 64 x 32 tiles.  With 64 x 64 tiles a symmetric n = 832 product has 91 CTAs for 148 SMs and each CTA
+// (4 warps) keeps the DMMA pipe only ~66 % busy (profiles/r02_ncu_full_scf_h2o64.txt: 44.9 us per product).  Half-width
+// tiles give 182 CTAs of half the work, two of which fit an SM (83 KB of shared memory each): every SM is busy and the SMs
+// that hold two CTAs overlap their latencies.  Same operands, same k order per element as k_gemm_nn<true>: identical bits.
+constexpr int kGemmBN2 = 32;
+constexpr int kGemmLdB2 = kGemmBN2 + 4;  // 36 (36 mod 16 = 4, see kGemmLdB)
+constexpr int kGemmStageDoubles2 = kGemmTile * kGemmLdA + kGemmBK * kGemmLdB2;
+constexpr size_t kGemmSmemBytes2 = (size_t)kGemmStages * kGemmStageDoubles2 * sizeof(double);
+
+__global__ void __launch_bounds__(kGemmThreads, 2) k_gemm_sym32(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int np,
+                                                                const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    extern __shared__ __align__(16) double gsm[];
+    const int nt = np / kGemmTile;
+    // row tile ti (64 rows) against the column tiles tj (32 columns) that reach the diagonal or lie above it: tj >= 2 ti
+    int b = blockIdx.x, ti = 0;
+    while (b >= 2 * (nt - ti)) {
+        b -= 2 * (nt - ti);
+        ti++;
+    }
+    const int tj = 2 * ti + b;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3;
+    const double* Ag = A + (size_t)ti * kGemmTile * np;
+    const double* Bg = B + (size_t)tj * kGemmBN2;
+    auto load_stage = [&](int s, int k0) {
+        double* As = gsm + (size_t)s * kGemmStageDoubles2;
+        double* Bs = As + kGemmTile * kGemmLdA;
+#pragma unroll
+        for (int c = tid; c < kGemmTile * kGemmBK / 2; c += kGemmThreads) {
+            const int r = c >> 4, cc = (c & 15) * 2;
+            cp_async16(As + r * kGemmLdA + cc, Ag + (size_t)r * np + k0 + cc);
+        }
+#pragma unroll
+        for (int c = tid; c < kGemmBK * kGemmBN2 / 2; c += kGemmThreads) {
+            const int r = c >> 4, cc = (c & 15) * 2;
+            cp_async16(Bs + r * kGemmLdB2 + cc, Bg + (size_t)(k0 + r) * np + cc);
+        }
+    };
+    double acc[4][2][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int n = 0; n < 2; n++) acc[mt][n][0] = acc[mt][n][1] = 0.0;
+    const int nk = np / kGemmBK;
+    for (int s = 0; s < kGemmStages - 1; s++) {
+        if (s < nk) load_stage(s, s * kGemmBK);
+        cp_async_commit();
+    }
+    for (int k = 0; k < nk; k++) {
+        cp_async_wait<kGemmStages - 2>();
+        __syncthreads();
+        const int kn = k + kGemmStages - 1;
+        if (kn < nk) load_stage(kn % kGemmStages, kn * kGemmBK);
+        cp_async_commit();
+        const double* As = gsm + (size_t)(k % kGemmStages) * kGemmStageDoubles2;
+        const double* Bs = As + kGemmTile * kGemmLdA;
+#pragma unroll
+        for (int kk = 0; kk < kGemmBK; kk += 4) {
+            double a[4], bb[2];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) a[mt] = As[(wm * 32 + mt * 8 + g) * kGemmLdA + kk + q];
+#pragma unroll
+            for (int n = 0; n < 2; n++) bb[n] = Bs[(kk + q) * kGemmLdB2 + wn * 16 + n * 8 + g];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int n = 0; n < 2; n++) dmma884(acc[mt][n][0], acc[mt][n][1], a[mt], bb[n]);
+        }
+    }
+    cp_async_wait<0>();
+    const int row0 = ti * kGemmTile + wm * 32 + g, col0 = tj * kGemmBN2 + wn * 16 + q * 2;
+    const bool above = tj * kGemmBN2 >= (ti + 1) * kGemmTile;  // the whole tile lies above the diagonal
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int n = 0; n < 2; n++) {
+            const int r = row0 + mt * 8, c = col0 + n * 8;
+            if (above) {
+                *reinterpret_cast<double2*>(C + (size_t)r * np + c) = make_double2(acc[mt][n][0], acc[mt][n][1]);
+                C[(size_t)c * np + r] = acc[mt][n][0];
+                C[(size_t)(c + 1) * np + r] = acc[mt][n][1];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    if (c + e >= r) {
+                        C[(size_t)r * np + c + e] = acc[mt][n][e];
+                        C[(size_t)(c + e) * np + r] = acc[mt][n][e];
+                    }
+            }
+        }
+}
+
+
 // dst[np][np] (zero padded) = a[nb][nb] (+ b[nb][nb])
 __global__ void k_scf_pad_sum(const double* __restrict__ a, const double* __restrict__ b, int nb, int np, double* __restrict__ dst) {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
