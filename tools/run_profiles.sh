@@ -8,12 +8,14 @@ O=gpurun_out
 T=${1:-r02}
 mkdir -p $O
 K='regex:k_contract_tma|k_rho_tma|k_interp_bin'
+if [ -z "$PROF_ONLY" ]; then   # PROF_ONLY=1: the ncu captures only
 python bench.py --steps 10 > $O/${T}_bench_h2o64.json 2> $O/${T}_bench_h2o64.err
 python bench.py --workload c40h82_fine --steps 10 --no-cpu-baseline > $O/${T}_bench_c40h82_fine.json 2> /dev/null
 python bench.py --workload h2o32 --steps 10 --no-cpu-baseline > $O/${T}_bench_h2o32.json 2> /dev/null
 python bench.py --workload benzene --steps 20 > $O/${T}_bench_benzene.json 2> /dev/null
 python bench.py --impl reference --steps 1 --warmup 0 > $O/${T}_bench_reference_h2o64.json 2> /dev/null
 python bench.py --workload c40h82 --steps 5 --no-cpu-baseline --no-scf > $O/${T}_bench_c40h82_1e7pts.json 2> $O/${T}_bench_c40h82_1e7pts.err
+fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/${T}_launches_h2o64.csv python tools/dev_prof_fock.py h2o64 3 > /dev/null 2>&1
 python tools/ncu_summary.py launches $O/${T}_launches_h2o64.csv $O/${T}_launches_h2o64.txt && rm -f $O/${T}_launches_h2o64.csv
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/${T}_launches_scf.csv python tools/dev_prof_scf.py h2o64 > /dev/null 2>&1
@@ -30,5 +32,5 @@ prof ${T}_prof_h2o64 "$K" 9 3 python tools/dev_prof_fock.py h2o64 2
 prof ${T}_prof_c40h82_fine "$K" 9 3 python tools/dev_prof_fock.py c40h82_fine 2
 prof ${T}_prof_c40h82_1e7pts "$K" 9 3 python tools/dev_prof_fock.py c40h82 2
 FAKE_RANK=0 FAKE_NRANKS=8 prof ${T}_prof_c40h82_1e7pts_shard0of8 "$K" 9 3 python tools/dev_prof_fock.py c40h82 2
-prof ${T}_prof_scf_h2o64 "regex:k_gemm_nn" 4 2 python tools/dev_prof_scf.py h2o64
+prof ${T}_prof_scf_h2o64 "regex:k_gemm_nn|k_gemm_sym32" 4 3 python tools/dev_prof_scf.py h2o64
 ls -la $O
