@@ -494,3 +494,76 @@ void oracle_hartree(oracle_t *o, double *J) {
         }
     free(A), free(xs), free(ys);
 }
+
+/* ---- density dump: src/rectangulargrid.cpp:34-80, src/cgf.cpp:67-94,164-172, src/gridpoint.cpp:82-109 ------------------ */
+/* GTO::get_grad as the reference evaluates it (separable exponentials, derivative of the monomial WITHOUT its factor l, no
+ * normalisation constant, contraction coefficient applied twice by CGF::get_grad); restated as written, not corrected. */
+static void cgf_grad(const oracle_t *o, int b, const double *r, double *g) {
+    g[0] = g[1] = g[2] = 0.0;
+    for (int k = o->bf_off[b]; k < o->bf_off[b + 1]; k++) {
+        const double al = o->alpha[k], c = o->coeff[k];
+        const int *lmn = o->lmn + 3 * k;
+        const double d[3] = {r[0] - o->bf_center[3 * b], r[1] - o->bf_center[3 * b + 1], r[2] - o->bf_center[3 * b + 2]};
+        double e[3], f[3], q[3];
+        for (int a = 0; a < 3; a++) {
+            e[a] = exp(-al * pow(d[a], 2));
+            f[a] = pow(d[a], lmn[a]) * e[a];
+            q[a] = -2.0 * al * d[a] * f[a];
+            if (lmn[a] > 0) q[a] += pow(d[a], lmn[a] - 1) * e[a];
+        }
+        g[0] += c * (c * q[0] * f[1] * f[2]);
+        g[1] += c * (c * f[0] * q[1] * f[2]);
+        g[2] += c * (c * f[0] * f[1] * q[2]);
+    }
+}
+
+/* RectangularGrid::build_grid(size, dp) + set_density(P): pos [dp^3][3], rho [dp^3], grad [dp^3][3]; P column-major nbf x nbf */
+void oracle_rect_density(const oracle_t *o, double size, int dp, const double *P, double *pos, double *rho, double *grad) {
+    const int nb = o->nbf;
+    const double gd = size / (double)(dp - 1);
+#pragma omp parallel
+    {
+        double *amp = dalloc(nb), *gr = dalloc(3 * (size_t)nb), *Pa = dalloc(nb), *Pg = dalloc(nb);
+#pragma omp for schedule(static)
+        for (long idx = 0; idx < (long)dp * dp * dp; idx++) {
+            const long k = idx % dp, j = (idx / dp) % dp, i = idx / ((long)dp * dp);
+            const double r[3] = {(double)k * gd - size / 2.0, (double)j * gd - size / 2.0, (double)i * gd - size / 2.0};
+            for (int c = 0; c < 3; c++) pos[3 * idx + c] = r[c];
+            for (int b = 0; b < nb; b++) {
+                amp[b] = cgf_amp(o, b, r);
+                double g3[3];
+                cgf_grad(o, b, r, g3);
+                for (int c = 0; c < 3; c++) gr[(size_t)c * nb + b] = g3[c];
+            }
+            /* rho = 2 amp . (P amp)   (src/gridpoint.cpp:82-84) */
+            for (int a = 0; a < nb; a++) {
+                double s = 0.0;
+                for (int b = 0; b < nb; b++) s += P[(size_t)b * nb + a] * amp[b];
+                Pa[a] = s;
+            }
+            double s = 0.0;
+            for (int a = 0; a < nb; a++) s += amp[a] * Pa[a];
+            rho[idx] = 2.0 * s;
+            /* g_c = 2 amp . (P d_c) + 2 d_c . (P amp)   (src/gridpoint.cpp:94-109) */
+            for (int c = 0; c < 3; c++) {
+                const double *dc = gr + (size_t)c * nb;
+                for (int a = 0; a < nb; a++) {
+                    double t = 0.0;
+                    for (int b = 0; b < nb; b++) t += P[(size_t)b * nb + a] * dc[b];
+                    Pg[a] = t;
+                }
+                double s1 = 0.0, s2 = 0.0;
+                for (int a = 0; a < nb; a++) {
+                    s1 += amp[a] * Pg[a];
+                    s2 += dc[a] * Pa[a];
+                }
+                grad[3 * idx + c] = 2.0 * s1 + 2.0 * s2;
+            }
+        }
+        free(amp);
+        free(gr);
+        free(Pa);
+        free(Pg);
+    }
+}
+

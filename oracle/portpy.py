@@ -39,6 +39,7 @@ def _lib():
         L.oracle_xc.argtypes = [C.c_void_p, _dp]
         L.oracle_xc.restype = C.c_double
         L.oracle_hartree.argtypes = [C.c_void_p, _dp]
+        L.oracle_rect_density.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, _dp, _dp, _dp]
         _L = L
     return _L
 
@@ -97,6 +98,15 @@ class Port:
         rho_lm, U_lm, V, Vf = np.zeros(n), np.zeros(n), np.zeros(self.npts), np.zeros(self.npts)
         _lib().oracle_get_hartree(self.h, rho_lm.ctypes.data_as(_dp), U_lm.ctypes.data_as(_dp), V.ctypes.data_as(_dp), Vf.ctypes.data_as(_dp))
         return J, dict(rho_lm=rho_lm, U_lm=U_lm, V=V, V_fuzzy=Vf)
+
+    def rect_density(self, size, dp, P):
+        """RectangularGrid::build_grid(size, dp) + set_density(P) (src/rectangulargrid.cpp:34-80)."""
+        P = np.asfortranarray(P, dtype=np.float64)
+        n = int(dp) ** 3
+        pos, rho, grad = np.zeros((n, 3)), np.zeros(n), np.zeros((n, 3))
+        _lib().oracle_rect_density(self.h, float(size), int(dp), P.ctypes.data_as(_dp), pos.ctypes.data_as(_dp), rho.ctypes.data_as(_dp),
+                                   grad.ctypes.data_as(_dp))
+        return pos, rho, grad
 
     def close(self):
         if self.h:

@@ -288,6 +288,29 @@ def test_c_restatement_matches_reference_golden(name):
     o.close()
 
 
+@pytest.mark.parametrize("name", ["h2o_sto3g", "benzene_p631_fine", "co_sto3g_coarse"])
+def test_c_restatement_of_the_density_dump_matches_reference(name):
+    """oracle_port.c's RectangularGrid restatement (density + the reference's own gradient expression, src/cgf.cpp:67-94) against
+    the fixture of the unmodified reference (tests/golden/make_golden_rect.py), non-symmetric P included."""
+    from oracle import portpy
+
+    if not portpy.available():
+        pytest.skip("oracle/liboracle.so not built")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "rect_density.npz"))
+    sysd = {k: z["%s.%s" % (name, k)] for k in ("Z", "xyz", "bf_nprim", "bf_center", "alpha", "coeff", "norm", "lmn")}
+    o = portpy.Port(sysd, 6, 0, 0)  # the dump needs the basis only: smallest atomic grid there is
+    size, dp = float(z[name + ".size"]), int(z[name + ".dp"])
+    pos, rho, grad = o.rect_density(size, dp, z[name + ".P"])
+    assert np.array_equal(pos, z[name + ".pos"])
+    assert np.max(np.abs(rho - z[name + ".rho"])) <= 1e-13 * np.max(np.abs(z[name + ".rho"]))
+    assert np.max(np.abs(grad - z[name + ".grad"])) <= 1e-13 * np.max(np.abs(z[name + ".grad"]))
+    if name + ".P_nonsym" in z:
+        _, rho_n, grad_n = o.rect_density(size, dp, z[name + ".P_nonsym"])
+        assert np.max(np.abs(rho_n - z[name + ".rho_nonsym"])) <= 1e-13 * np.max(np.abs(z[name + ".rho_nonsym"]))
+        assert np.max(np.abs(grad_n - z[name + ".grad_nonsym"])) <= 1e-13 * np.max(np.abs(z[name + ".grad_nonsym"]))
+    o.close()
+
+
 @pytest.mark.parametrize("nz", [2, 1], ids=["xc_and_j", "fused_fock"])
 @pytest.mark.parametrize("nbp,nchunk,nsm", [(32, 155, 148), (96, 1095, 148), (832, 16800, 148), (832, 2100, 148), (544, 312000, 148),
                                            (2048, 5000, 148), (832, 0, 148), (128, 3, 148), (832, 16800, 7), (448, 9000, 148)])
