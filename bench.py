@@ -326,6 +326,7 @@ def main():
     single_process = world == 1 and args.gpus > 1
     ngpus_total = args.gpus if single_process else world
     if args.no_peer:
+        os.environ["DFTGRID_DEVELOPER"] = "1"
         os.environ["DFTGRID_NO_PEER"] = "1"
     dist = None
     comm_id = None

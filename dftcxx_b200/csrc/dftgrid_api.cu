@@ -35,6 +35,10 @@ namespace {
 
 thread_local std::string g_error;
 
+// Developer switches (A/B measurements, tools/dev_*; listed at the end of DESIGN.md) are honoured only when DFTGRID_DEVELOPER
+// is set: a stray environment variable cannot change what a production run does.
+const char* dev_env(const char* name) { return std::getenv("DFTGRID_DEVELOPER") ? std::getenv(name) : nullptr; }
+
 struct CudaError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
@@ -235,7 +239,7 @@ void allreduce(dftgrid* h, double* buf, size_t count) {
     if (h->nranks == 1) return;
     if (!h->comm) {
         // developer switch: time one shard's kernels on a single GPU (results are then partial sums, not the molecule's)
-        if (std::getenv("DFTGRID_DEBUG_SKIP_COMM")) return;
+        if (dev_env("DFTGRID_DEBUG_SKIP_COMM")) return;
         throw std::runtime_error("nranks > 1 but dftgrid_comm_init was not called");
     }
     int rc = nccl_api().AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
@@ -330,12 +334,12 @@ void compute_contract_schedule(int nbp, long nchunk, int nsm, int nz, ContractSc
     S.npairs = (int)S.pairs.size() / 2;
     const int npairs = S.npairs, nitems = nz * npairs;
     std::vector<double> cost(nitems);
-    static const char* nc = std::getenv("DFTGRID_NARROW_COST");  // developer sweeps of the cost model
-    static const char* dc = std::getenv("DFTGRID_DIAG_COST");
-    static const char* ec = std::getenv("DFTGRID_EDGE_DIAG_COST");
-    static const char* l2e = std::getenv("DFTGRID_L2_BLOCK_MB");
-    static const char* n32c = std::getenv("DFTGRID_N32_COST");
-    static const char* d32c = std::getenv("DFTGRID_D32_COST");
+    static const char* nc = dev_env("DFTGRID_NARROW_COST");  // developer sweeps of the cost model
+    static const char* dc = dev_env("DFTGRID_DIAG_COST");
+    static const char* ec = dev_env("DFTGRID_EDGE_DIAG_COST");
+    static const char* l2e = dev_env("DFTGRID_L2_BLOCK_MB");
+    static const char* n32c = dev_env("DFTGRID_N32_COST");
+    static const char* d32c = dev_env("DFTGRID_D32_COST");
     double W1 = 0.0;  // cost of all items for one chunk
     for (int it = 0; it < nitems; it++) {
         const int ti = S.pairs[2 * (it % npairs)], tj = S.pairs[2 * (it % npairs) + 1];
@@ -434,7 +438,7 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector
         D.cta_off.upload(S.cta_off, st);
         D.item_off.upload(S.item_off, st);
         max_segs = std::max(max_segs, S.segs.size());
-        if (std::getenv("DFTGRID_DEBUG_CTA_TIMES") && k == 1)  // developer instrumentation: the fused schedule's segments per CTA
+        if (dev_env("DFTGRID_DEBUG_CTA_TIMES") && k == 1)  // developer instrumentation: the fused schedule's segments per CTA
             for (int c = 0; c + 1 < (int)S.cta_off.size(); c++) {
                 std::fprintf(stderr, "[dftgrid] sched cta %3d:", c);
                 for (int q = S.cta_off[c]; q < S.cta_off[c + 1]; q++)
@@ -449,9 +453,9 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector
         // soft lockstep of the sweep (kernels_dense.cuh: ConSync): windows of 24 MB of Phi rows, at most 2 windows of lead
         // (developer switches DFTGRID_CON_SYNC_MB, 0 = off, _LEAD, _PCT); only when the sweep has enough windows.  Measured at
         // (H2O)64 on the calibrated shares: DRAM reads 7.0 -> 4.7 GB per launch (1.26x the algorithmic 3.73 GB), 8.73 -> 8.62 ms
-        static const char* mb = std::getenv("DFTGRID_CON_SYNC_MB");
-        static const char* lead = std::getenv("DFTGRID_CON_SYNC_LEAD");
-        static const char* pct = std::getenv("DFTGRID_CON_SYNC_PCT");
+        static const char* mb = dev_env("DFTGRID_CON_SYNC_MB");
+        static const char* lead = dev_env("DFTGRID_CON_SYNC_LEAD");
+        static const char* pct = dev_env("DFTGRID_CON_SYNC_PCT");
         const double sync_mb = mb ? std::atof(mb) : 24.0;
         const double chunk_bytes = (double)kTileK * h->nbp * sizeof(double);
         h->con_sync_wc = 0;
@@ -477,9 +481,9 @@ void build_contract_schedule(dftgrid* h, long nchunk, int nsm, const std::vector
 // The launch costs as much as one contraction, once per grid.  Results do not depend on it (any schedule sums the same
 // partial tiles in a fixed order); DFTGRID_NO_CALIBRATE keeps the analytic model.
 void calibrate_contract_costs(dftgrid* h, int nsm, const std::vector<double>& sig_frac, const std::vector<double>& item_frac) {
-    if (std::getenv("DFTGRID_NO_CALIBRATE") || h->n_active_chunks < 4L * nsm) return;
+    if (dev_env("DFTGRID_NO_CALIBRATE") || h->n_active_chunks < 4L * nsm) return;
     cudaStream_t st = h->stream;
-    const bool verbose = std::getenv("DFTGRID_DEBUG_CTA_TIMES") != nullptr;
+    const bool verbose = dev_env("DFTGRID_DEBUG_CTA_TIMES") != nullptr;
     // one instrumented run of the CURRENT fused schedule: kernel span in us, per-CTA (duration us, stages)
     auto measure = [&](std::vector<double>& us, std::vector<double>& stages) -> double {
         const dftgrid::DevSchedule& D = h->sched[1];
@@ -576,8 +580,8 @@ void build_active_lists(dftgrid* h, int nsm) {
     // Screening map (k_chunk_masks).  DFTGRID_SCREEN_TAU: threshold on |phi| (default 1e-20; 0 = exact zeros only; negative
     // or DFTGRID_NO_ZERO_SKIP = no skipping at all, developer A/B switches).  More than 64 column blocks: no map.
     double tau = 1e-20;
-    if (const char* e = std::getenv("DFTGRID_SCREEN_TAU")) tau = std::atof(e);
-    const bool screen = nchunk > 0 && tau >= 0.0 && nblk <= 64 && !std::getenv("DFTGRID_NO_ZERO_SKIP");
+    if (const char* e = dev_env("DFTGRID_SCREEN_TAU")) tau = std::atof(e);
+    const bool screen = nchunk > 0 && tau >= 0.0 && nblk <= 64 && !dev_env("DFTGRID_NO_ZERO_SKIP");
     std::vector<unsigned long long> masks((size_t)nchunk, ~0ull);
     if (screen) {
         DevBuf<unsigned long long> d_masks;
@@ -640,7 +644,7 @@ void build_active_lists(dftgrid* h, int nsm) {
         // A staged chunk never costs less than the pipeline's own turnaround (the producers' ~33 bulk copies each, the
         // barrier round trip): a floor on the per-stage fraction, calibrated by sweeps (DFTGRID_STAGE_FLOOR).
         double floor_ = 0.25;
-        if (const char* e = std::getenv("DFTGRID_STAGE_FLOOR")) floor_ = std::atof(e);
+        if (const char* e = dev_env("DFTGRID_STAGE_FLOOR")) floor_ = std::atof(e);
         const int nt = (h->nbp + kTileM - 1) / kTileM;
         for (int ti = 0; ti < nt; ti++)
             for (int tj = ti; tj < nt; tj++) {
@@ -673,7 +677,7 @@ void build_active_lists(dftgrid* h, int nsm) {
         const double waves = (double)((h->n_active_chunks + 3) / 4) / (double)nsm;
         const int nslab = (h->nbp + kTileN - 1) / kTileN;
         int split = waves >= 40.0 ? 1 : (waves >= 12.0 ? 2 : 3);  // measured at (H2O)64: 28 waves 11.07 -> 10.98 ms (2 CTAs), 3.5 waves 1.56 -> 1.46 ms (3 CTAs)
-        if (const char* e = std::getenv("DFTGRID_RHO_SPLIT")) split = std::atoi(e);  // developer A/B switch
+        if (const char* e = dev_env("DFTGRID_RHO_SPLIT")) split = std::atoi(e);  // developer A/B switch
         h->rho_split = std::max(1, std::min(split, std::min(nslab, 3)));
         h->rho_part_stride = (size_t)g.nloc + 64;
         if (h->rho_split > 1) {
@@ -683,7 +687,7 @@ void build_active_lists(dftgrid* h, int nsm) {
     }
     build_contract_schedule(h, h->n_active_chunks, nsm, item_frac.empty() ? nullptr : &item_frac);
     if (!item_frac.empty()) calibrate_contract_costs(h, nsm, sig_frac, item_frac);
-    if (std::getenv("DFTGRID_DEBUG_CTA_TIMES")) {
+    if (dev_env("DFTGRID_DEBUG_CTA_TIMES")) {
         h->d_dbg_times.alloc(3 * (size_t)nsm + 3);
         for (size_t i = 0; i < item_frac.size(); i++) std::fprintf(stderr, "[dftgrid] pair %zu work fraction %.3f\n", i, item_frac[i]);
     }
@@ -696,7 +700,7 @@ void build_pair_bins(dftgrid* h) {
     const GridShape& g = h->g;
     cudaStream_t st = h->stream;
     h->binned = false;
-    if (std::getenv("DFTGRID_INTERP_POINTWISE")) return;  // developer A/B switch
+    if (dev_env("DFTGRID_INTERP_POINTWISE")) return;  // developer A/B switch
     if (!(g.lmax == 5 || g.lmax == 8 || g.lmax == 10 || g.lmax == 11)) return;
     if (g.nloc == 0 || g.natoms < 2) return;
     const int nkeys = g.natoms * g.nrad;
@@ -704,12 +708,12 @@ void build_pair_bins(dftgrid* h) {
     CK(cudaMemGetInfo(&mem_free, &mem_total));
     // pairs per lane: 3 when the pairs' geometry can be kept (k_pair_geometry: the kernel then has the registers for a third
     // pair per lane, measured 5.73 -> 5.48 ms at (H2O)64), 2 otherwise; DFTGRID_INTERP_R overrides (developer switch)
-    static const bool no_geo = std::getenv("DFTGRID_NO_PAIR_GEO") != nullptr;  // developer A/B switch
+    static const bool no_geo = dev_env("DFTGRID_NO_PAIR_GEO") != nullptr;  // developer A/B switch
     const double pairs_est = (double)g.nloc * (g.natoms - 1) + (double)nkeys * 96.0;
     const double lists = pairs_est * 12.0 + (double)g.nloc * g.natoms * 4.0;
     const bool want_geo = !no_geo && lists + pairs_est * 48.0 < 0.8 * (double)mem_free;  // nothing large is allocated after this
     h->bin_R = want_geo ? 3 : 2;
-    if (const char* r = std::getenv("DFTGRID_INTERP_R")) h->bin_R = std::atoi(r);
+    if (const char* r = dev_env("DFTGRID_INTERP_R")) h->bin_R = std::atoi(r);
     if (h->bin_R < 2 || h->bin_R > 4) h->bin_R = 2;
     const int unit = 32 * h->bin_R;
     const double pairs_max = (double)g.nloc * (g.natoms - 1) + (double)nkeys * unit;
@@ -773,9 +777,9 @@ void build_pair_bins(dftgrid* h) {
 // arithmetic on replicated data: every rank computes the same cuts.  Single rank, or screening off: the plain rule.
 void shard_shells(dftgrid* h, const std::vector<double>& rtab, long nshell, long* first, long* count) {
     double tau = 1e-20;
-    if (const char* e = std::getenv("DFTGRID_SCREEN_TAU")) tau = std::atof(e);
+    if (const char* e = dev_env("DFTGRID_SCREEN_TAU")) tau = std::atof(e);
     const int nblk = h->nbp / 32;
-    if (h->nranks == 1 || tau < 0.0 || nblk > 64 || std::getenv("DFTGRID_NO_ZERO_SKIP") || std::getenv("DFTGRID_EQUAL_SHARDS")) {
+    if (h->nranks == 1 || tau < 0.0 || nblk > 64 || dev_env("DFTGRID_NO_ZERO_SKIP") || dev_env("DFTGRID_EQUAL_SHARDS")) {
         dftgrid_shard_range(nshell, h->rank, h->nranks, first, count);
         return;
     }
@@ -847,7 +851,7 @@ void do_build(dftgrid* h) {
     const long nshell = (long)g.natoms * g.nrad;
     h->leb_off = lebedev_offset(prm.lebedev_order);
     // developer instrumentation (DFTGRID_DEBUG_BUILD_TIMES): wall clock of the build's host-side milestones
-    static const bool build_times = std::getenv("DFTGRID_DEBUG_BUILD_TIMES") != nullptr;
+    static const bool build_times = dev_env("DFTGRID_DEBUG_BUILD_TIMES") != nullptr;
     auto t_mark = std::chrono::steady_clock::now();
     auto mark = [&](const char* what) {
         if (!build_times) return;
@@ -1188,7 +1192,7 @@ void run_potential(dftgrid* h) {
         }                                                                                                       \
         break;
             const bool geo = h->d_pair_geo.p != nullptr;
-            static const bool five = std::getenv("DFTGRID_INTERP_MINB5") != nullptr;  // developer A/B switch
+            static const bool five = dev_env("DFTGRID_INTERP_MINB5") != nullptr;  // developer A/B switch
             switch (g.lmax) {
                 DFG_BIN_CASE(5)
                 DFG_BIN_CASE(8)
@@ -1427,7 +1431,7 @@ void require_density(dftgrid* h) {
 // too: the peer-memory kernels read their epoch from device memory and NCCL collectives are capturable.
 void run_iteration_device(dftgrid* h, int mode) {
     if (!h->built) throw std::runtime_error("dftgrid_build has not been called");
-    static const bool no_graph = std::getenv("DFTGRID_NO_GRAPH") != nullptr;  // developer A/B switch
+    static const bool no_graph = dev_env("DFTGRID_NO_GRAPH") != nullptr;  // developer A/B switch
     dftgrid::IterGraph& G = h->graphs[mode];
     const bool want_graph = !no_graph && !G.failed && mode != kModeFockJ;
     auto mark = [&] {
@@ -1796,7 +1800,7 @@ int dftgrid_create_multi(dftgrid_t** out, const dftgrid_system* sys, const dftgr
                 int can = 1;
                 if (a != b && (cudaDeviceCanAccessPeer(&can, devs[a], devs[b]) != cudaSuccess || !can)) p2p = false;
             }
-        static const bool no_peer = std::getenv("DFTGRID_NO_PEER") != nullptr;  // developer A/B switch
+        static const bool no_peer = dev_env("DFTGRID_NO_PEER") != nullptr;  // developer A/B switch
         if (p2p && !no_peer) {
             int prc = gh->group->run([&](dftgrid* s, int r) -> int {
                 return guarded([&] {

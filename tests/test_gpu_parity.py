@@ -381,6 +381,7 @@ def test_binned_and_point_parallel_interpolation_agree(monkeypatch):
         Jb = mg.calculate_hartree_potential()
     finally:
         mg.close()
+    monkeypatch.setenv("DFTGRID_DEVELOPER", "1")
     monkeypatch.setenv("DFTGRID_INTERP_POINTWISE", "1")
     mp = make_grid(g)
     try:

@@ -12,15 +12,20 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def run(name, tau):
+def run(name, tau, developer=True):
     from dftcxx_b200.grid import MolecularGrid
     from dftcxx_b200.systems import WORKLOADS, synthetic_density
 
     old = os.environ.get("DFTGRID_SCREEN_TAU")
+    old_dev = os.environ.get("DFTGRID_DEVELOPER")
     if tau is None:
         os.environ.pop("DFTGRID_SCREEN_TAU", None)
     else:
         os.environ["DFTGRID_SCREEN_TAU"] = repr(tau)
+    if developer:
+        os.environ["DFTGRID_DEVELOPER"] = "1"  # the library honours its developer switches only with this set
+    else:
+        os.environ.pop("DFTGRID_DEVELOPER", None)
     try:
         fac, prm = WORKLOADS[name]
         mol = fac()
@@ -38,6 +43,10 @@ def run(name, tau):
             os.environ.pop("DFTGRID_SCREEN_TAU", None)
         else:
             os.environ["DFTGRID_SCREEN_TAU"] = old
+        if old_dev is None:
+            os.environ.pop("DFTGRID_DEVELOPER", None)
+        else:
+            os.environ["DFTGRID_DEVELOPER"] = old_dev
     return dict(J=J, XC=XC, F=F, rho=rho, exc=exc, nel=nel, ej=ej, frac=frac)
 
 
@@ -67,3 +76,12 @@ def test_screening_thresholds(name):
     dJ = np.max(np.abs(loose["J"] - off["J"]))
     assert 1e-14 < dJ < 1e-3, dJ
     print(name, "work fraction: exact %.3f default %.3f loose %.3f; dJ(loose) %.2e" % (exact["frac"], dflt["frac"], loose["frac"], dJ))
+
+
+def test_developer_switches_are_ignored_without_the_master_switch():
+    """A stray DFTGRID_* variable must not change a production run: without DFTGRID_DEVELOPER the library does not read them."""
+    ref = run("h2o32", None)
+    off = run("h2o32", -1.0)                       # developer mode: screening off
+    stray = run("h2o32", -1.0, developer=False)    # same variable, master switch absent: ignored
+    assert off["frac"] == 1.0 and ref["frac"] < 1.0
+    assert stray["frac"] == ref["frac"] and np.array_equal(stray["rho"], ref["rho"])

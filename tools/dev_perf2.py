@@ -1,6 +1,8 @@
 """Developer script (round 2): per-phase device timings of the two-matrix iteration, the fused Fock build and the
 device-resident SCF step for a synthetic workload.  usage: dev_perf2.py <workload> [ngpus]"""
 import os
+
+os.environ.setdefault("DFTGRID_DEVELOPER", "1")  # developer script: the library's A/B switches are live
 import sys
 import time
 

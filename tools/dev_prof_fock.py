@@ -1,5 +1,7 @@
 """Developer script: a few fused Fock builds of a workload (for ncu captures of the iteration kernels)."""
 import os
+
+os.environ.setdefault("DFTGRID_DEVELOPER", "1")  # developer script: the library's A/B switches are live
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,5 +1,7 @@
 """Developer script: a few device-resident SCF steps of a workload with a synthetic H / X (for ncu captures of k_gemm_nn / k_pm_*)."""
 import os
+
+os.environ.setdefault("DFTGRID_DEVELOPER", "1")  # developer script: the library's A/B switches are live
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -2,6 +2,8 @@
 density dump.  usage: dev_setup_times.py <workload>"""
 import ctypes
 import os
+
+os.environ.setdefault("DFTGRID_DEVELOPER", "1")  # developer script: the library's A/B switches are live
 import sys
 import time
 

@@ -1,6 +1,8 @@
 """Developer sweep of the contraction cost-model constants (environment switches) on a workload: prints the contraction time."""
 import itertools
 import os
+
+os.environ.setdefault("DFTGRID_DEVELOPER", "1")  # developer script: the library's A/B switches are live
 import re
 import subprocess
 import sys

@@ -3,6 +3,7 @@
 # (H2O)64, C40H82/fine, C40H82 at 10^7 points (whole and a 1/8 shard) and of the SCF algebra kernels.  The .ncu-rep files are
 # summarised on the box (gpurun returns at most 64 MiB) and removed; outputs: gpurun_out/${T}_*.
 # usage: tools/run_profiles.sh [tag]   (default tag r02)
+export DFTGRID_DEVELOPER=1  # the library honours its developer switches only with this set
 set -x
 O=gpurun_out
 T=${1:-r02}
