@@ -24,7 +24,7 @@ from dftcxx_b200.molecule import DATA  # noqa: E402
 from dftcxx_b200.systems import synthetic_density  # noqa: E402
 from oracle.refpy import Ref  # noqa: E402
 
-CASES = [("h2o_sto3g", None, 5.0, 15), ("benzene_p631_fine", None, 12.0, 9), ("co_sto3g_coarse", None, 6.0, 11)]
+CASES = [("h2o_sto3g", 5.0, 15), ("benzene_p631_fine", 12.0, 9), ("co_sto3g_coarse", 6.0, 11)]
 
 
 class _M:
@@ -34,16 +34,8 @@ class _M:
 
 def main():
     out = {"cases": np.array([c[0] for c in CASES])}
-    for name, text, size, dp in CASES:
-        if text is None:
-            path = os.path.join(DATA, "molecules", name + ".in")
-            r = Ref(path)
-        else:
-            with tempfile.NamedTemporaryFile("w", suffix=".in", delete=False) as f:
-                f.write(text)
-                path = f.name
-            r = Ref(path)
-            os.remove(path)
+    for name, size, dp in CASES:
+        r = Ref(os.path.join(DATA, "molecules", name + ".in"))
         for k, v in r.system().items():
             out["%s.%s" % (name, k)] = np.asarray(v)
         P = synthetic_density(_M(r.nbf, r.nelec))
