@@ -176,8 +176,8 @@ def reference_fit(workload, mol, prm, threads, whole=False):
             "least-squares fitted to the reference's loop bounds (Hartree ~ Npts*(Natoms-1)*nlm, rho+XC ~ Npts*nb^2), fit residuals %s; "
             "evaluated at the full workload: EXTRAPOLATED lower bound (single-sample extrapolations: %s s); the nb^2 terms run on the "
             "header shim, whose row-major mirror makes the reference's strided nb^2 dot products contiguous (a real Eigen build is slower there: "
-            "the CPU figure errs on the fast side); the same fit evaluated at (H2O)32 in the build container gave 225.7 s against 214.2 s for the "
-            "whole workload really run there (profiles/r02e_bench_reference_whole_h2o32_build_container.json)" % ("/".join(str(x) for x in sizes), "/".join("%.1f" % (t / 1e3) for t in ts),
+            "the CPU figure errs on the fast side); the same fit on the build container's 8 cores gave 225.7 s for (H2O)32 and 1281.8 s for (H2O)64 against "
+            "214.2 s and 1331.5 s for the WHOLE workloads really run there (profiles/r02e_bench_reference_whole_*_build_container.json)" % ("/".join(str(x) for x in sizes), "/".join("%.1f" % (t / 1e3) for t in ts),
                                                          "/".join("%+.1f%%" % (100 * r) for r in resid), "/".join("%.0f" % (v / 1e3) for v in lo_hi)))
     return float(full), desc, {"extrapolated": True, "measured_s": [t / 1e3 for t in ts], "sample_molecules": list(sizes), "a_ms": a, "b_ms": b,
                                "fit_residuals": resid, "single_sample_extrapolations_ms": lo_hi}
