@@ -1,6 +1,7 @@
 // Closed-shell LDA Kohn-Sham SCF driver: the reference's DFT class (src/dft.h, src/dft.cpp) with the grid work
-// delegated to the GPU MolecularGrid.  One-electron integrals, the canonical orthogonalisation, the eigen-solve,
-// density mixing and the energy expression stay on the host exactly as in the reference.
+// delegated to the GPU MolecularGrid.  The canonical orthogonalisation stays on the host; the one-electron integrals come
+// from the device unless `integrals = host`; the eigen-solve, density mixing and energy expression run on the device by
+// default (scf = device) or on the host exactly as in the reference (scf = host).
 #pragma once
 #include <memory>
 #include <string>

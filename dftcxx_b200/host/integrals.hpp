@@ -1,5 +1,6 @@
 // One-electron integrals over contracted Cartesian Gaussians (s, p, d): overlap, kinetic energy and nuclear
-// attraction.  They stay on the host, as in the reference (src/integrals.cpp; north_star).  The evaluation scheme
+// attraction: the host path (`integrals = host`; the default takes them from the device, csrc/kernels_integrals.cuh, which
+// evaluates the same closed forms) and the CPU-testable statement of the scheme.  The evaluation scheme
 // here is McMurchie-Davidson (Hermite expansion coefficients E_t^{ij} and Hermite Coulomb integrals R_tuv), not the
 // reference's Taketa-Huzinaga-O-ohata sums; both are exact closed forms in the Boys function, so the numbers agree
 // to rounding provided the reference's two numerical conventions are kept:
